@@ -1,0 +1,39 @@
+# Top-level build: everything is compiled in-tree for sm_100a only.
+#   make lib      -> kmer_id_b200/libkmerid_b200.so   (CUDA kernels + C-ABI, include/kmer_id.h)
+#   make host     -> kmer_id_b200/bin/nk10            (C++ drop-in for the reference's ./nk10 <dir/>)
+#   make tools    -> tools/libkidsynth.so, tools/kid_synth (synthetic DB / read generators)
+#   make oracle   -> oracle/liboracle.so (+ oracle/_ref/* when /root/reference is present)
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+CXXFLAGS  := -O3 -std=c++17 -Wall -Wextra -fPIC -pthread
+CUDA_HOME ?= /usr/local/cuda
+
+CSRC := kmer_id_b200/csrc
+LIB  := kmer_id_b200/libkmerid_b200.so
+LIB_OBJS := $(CSRC)/kid_api.o $(CSRC)/kid_classify.o $(CSRC)/kid_build.o $(CSRC)/kid_sample.o
+
+all: lib tools host oracle
+
+lib: $(LIB)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kid_common.cuh $(CSRC)/kid_kernels.cuh include/kmer_id.h
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(LIB_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS)
+
+host: lib
+	@if [ -f kmer_id_b200/host/Makefile ]; then $(MAKE) --no-print-directory -C kmer_id_b200/host; fi
+
+tools: lib
+	@if [ -f tools/Makefile ]; then $(MAKE) --no-print-directory -C tools; fi
+
+oracle:
+	$(MAKE) --no-print-directory -C oracle all
+
+clean:
+	rm -f $(LIB_OBJS) $(LIB)
+	-$(MAKE) -C oracle clean
+.PHONY: all lib host tools oracle clean

@@ -1,0 +1,140 @@
+/*
+ * kmer_id.h - C-ABI of libkmerid_b200.so, the sm_100a implementation of kmer_id's
+ * read-classification hot path.
+ *
+ * The reference (/root/reference/newkmer_10nx.cpp) has no plugin or FFI layer: it is one
+ * executable with global state.  Each entry point below therefore replaces an *internal seam* of
+ * that file, named per function as "replaces newkmer_10nx.cpp:<lines>".  A maintainer of the
+ * reference would bind these from main()/process_fqgz().
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative KID_E* code;
+ *     kid_last_error() returns the message for the calling thread's most recent failure.
+ *   - "device pointer" arguments are CUDA global-memory addresses on the db's device.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with KID_ECUDA.
+ *   - a kid_db is immutable after build and may be shared by several kid_sample objects; a
+ *     kid_sample is used from one host thread at a time.
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef KMER_ID_H
+#define KMER_ID_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KID_KSIZE 30 /* newkmer_10nx.cpp:43 */
+
+#define KID_OK 0
+#define KID_EINVAL (-1)  /* bad argument */
+#define KID_ECUDA (-2)   /* CUDA runtime error / no device */
+#define KID_ENOMEM (-3)  /* host or device allocation failed */
+#define KID_ERANGE (-4)  /* taxon id or tree node outside [0, n_taxa) (UB in the reference) */
+#define KID_ETREE (-5)   /* taxonomy has a cycle that never reaches the root (reference hangs) */
+#define KID_EFULL (-6)   /* table could not place every key (reference: "out of memory in table") */
+
+/* flags for kid_db_build */
+#define KID_DB_ACCEPT_U 1u /* reads: U/u count as T (kmer_read_vf6.cpp:496-500,521-525) */
+
+typedef struct kid_db kid_db;         /* GPU-resident probe table + taxonomy tree */
+typedef struct kid_sample kid_sample; /* per-sample accumulators: gcount, seen flags, counters */
+
+const char *kid_last_error(void);
+int kid_device_count(int *n);
+const char *kid_version(void);
+
+/* ---- database ------------------------------------------------------------------------------
+ * kid_db_build: replaces Hashtable::Hashtable/add_kmer (newkmer_10nx.cpp:173-180, 235-263) as
+ * driven by process_kmer (:619-661), and Tree1 (:93-154) as filled by main():973-983.
+ *   keys[i], taxa[i]  i = 0..n_keys-1, in FILE ORDER: one entry per forward 30-window of every
+ *                     parsed probe line, key = the 60-bit forward encoding (:634-646).
+ *                     Semantics reproduced: the first entry of a key wins, entries with
+ *                     taxa[i] == 0 are invisible.  taxa[i] >= n_taxa -> KID_ERANGE.
+ *   parent[t]         t = 0..n_taxa-1: Tree1::parent after all add_edge calls (default 1, :103).
+ *   keys_on_device    non-zero if keys/taxa are device pointers (then they are read in place).
+ *   log2_buckets      0 = choose from n_keys (load <= ~1/4 of 4-slot buckets); else 22..32.
+ */
+int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
+                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_buckets,
+                 void *stream, kid_db **out);
+void kid_db_free(kid_db *db);
+int kid_db_n_taxa(const kid_db *db);
+int kid_db_device(const kid_db *db);
+/* distinct visible keys, table buckets (32-byte sectors), table bytes, keys living outside their
+ * home bucket */
+int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets,
+                 uint64_t *table_bytes, uint64_t *n_displaced);
+/* Hashtable::getHash (:204-233) for n host keys -> host taxa (0 = absent). Test/diagnostic hook. */
+int kid_db_lookup(const kid_db *db, const uint64_t *keys, size_t n, uint32_t *taxa_out);
+/* Tree1::msca (:118-144) for n host pairs (x[i], y[i]) evaluated by the device routine. */
+int kid_db_msca(const kid_db *db, const int32_t *x, const int32_t *y, size_t n, int32_t *out);
+/* device address and size in 32-bit words of the table (for microbenchmarks such as the random
+ * sector-gather ceiling in bench.py) */
+int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_buckets);
+
+/* ---- per-sample state ----------------------------------------------------------------------
+ * replaces the globals gcount[], ucount[], kmer_seen (newkmer_10nx.cpp:61-64) and their reset in
+ * main():1017-1023.  seen flags are one bit per table slot, n_seen_words 32-bit words. */
+int kid_sample_create(const kid_db *db, kid_sample **out);
+void kid_sample_free(kid_sample *s);
+int kid_sample_begin(kid_sample *s, void *stream); /* zero gcount/seen/counters, asynchronously */
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * kid_classify_device: replaces process_qual (:714-760) + process_read (:452-617) +
+ * getHash/msca for a whole batch, ON THE GIVEN STREAM, with every buffer already on the device.
+ *   seq, qual   device byte buffers; read r occupies [off[r], off[r+1]) in both (same offsets).
+ *               qual == NULL: no trimming, reads need length > 30 (process_fagz :849-852).
+ *               Both buffers must be readable for 16 bytes past off[n_reads] (padding).
+ *   off         device uint64[n_reads+1]
+ *   out_taxon   device int32[n_reads] or NULL: final_targ (:616), or -1 if the read was dropped
+ *               by the length rule (:755) and therefore not counted anywhere.
+ *   out_span    device uint32[2*n_reads] or NULL: trimmed (start, stop) (:724-753)
+ * Accumulates gcount, seen flags and the lookup/hit counters into s.  Asynchronous. */
+int kid_classify_device(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
+                        const uint64_t *off, size_t n_reads, int32_t *out_taxon,
+                        uint32_t *out_span, void *stream);
+
+/* kid_classify_host: same, from HOST buffers (pinned or pageable; pinned overlaps copies with
+ * compute).  Splits the batch into chunks, double-buffers H2D copy / kernel / D2H copy on two
+ * internal streams and returns when out_* are complete.  This is the call a FASTQ reader makes
+ * per batch (replaces the per-record process_qual call at newkmer_10nx.cpp:800). */
+int kid_classify_host(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
+                      const uint64_t *off, size_t n_reads, int32_t *out_taxon,
+                      uint32_t *out_span);
+/* tuning knob for kid_classify_host: reads per chunk (default 1<<18) */
+int kid_sample_set_chunk_reads(kid_sample *s, size_t chunk_reads);
+/* bytes moved by kid_classify_host since kid_sample_begin (for bench.py's e2e accounting) */
+int kid_sample_transfer_bytes(const kid_sample *s, uint64_t *h2d, uint64_t *d2h);
+
+/* ---- sample end -------------------------------------------------------------------------------
+ * kid_sample_counts: replaces the read-out loop main():1040-1043.  Computes ucount as the
+ * per-taxon histogram of seen flags (equivalent to :596-603) and copies
+ * gcount/ucount (int32[n_taxa]) to the host.  Synchronous.  Either pointer may be NULL. */
+int kid_sample_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *stream);
+/* number of getHash calls (:529), hits (target > 0) and reads counted in gcount ("tct", :614) */
+int kid_sample_counters(kid_sample *s, uint64_t *lookups, uint64_t *hits, uint64_t *reads,
+                        void *stream);
+
+/* ---- multi-GPU building blocks (one process per GPU; the exchange itself is the caller's:
+ * NCCL / peer memory).  gcount is additive across shards; ucount is NOT: the
+ * seen flags must be OR-ed across ranks before they are histogrammed. */
+/* device address of gcount (int32[n_taxa]) - to be sum-all-reduced in place by the caller */
+int kid_sample_gcount_device(kid_sample *s, int32_t **gcount);
+/* device address of the seen bitmap (uint32[n_words]); words are padded so n_words % 1024 == 0 */
+int kid_sample_seen_device(kid_sample *s, uint32_t **seen, uint64_t *n_words);
+/* OR `n_src` bitmaps' word range [word0, word0+n) into dst (device pointers, possibly peer
+ * memory mapped over NVLink): dst[i] = src[0][word0+i] | ... ; dst may alias a src range. */
+int kid_seen_or_device(const kid_db *db, uint32_t *dst, const uint32_t *const *src, int n_src,
+                       uint64_t word0, uint64_t n_words, void *stream);
+/* ucount_partial[t] += #set flags in seen[word0 .. word0+n) whose slot holds taxon t
+ * (device int32[n_taxa], NOT zeroed here).  With disjoint word ranges per rank the partial
+ * histograms are additive, so a sum-all-reduce finishes the job. */
+int kid_ucount_range_device(const kid_db *db, const uint32_t *seen, uint64_t word0,
+                            uint64_t n_words, int32_t *ucount_partial, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMER_ID_H */

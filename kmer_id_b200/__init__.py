@@ -1,0 +1,236 @@
+"""kmer_id_b200 - B200 (sm_100a) implementation of kmer_id's nk10 read-classification path.
+
+This package is a thin ctypes binding over ``libkmerid_b200.so`` (C-ABI in ``include/kmer_id.h``).
+It exists for the tests and ``bench.py``; the product host is the C++ ``nk10`` drop-in under
+``kmer_id_b200/host``.  There is no CPU fallback: importing works without a GPU (so the symbol
+table can be checked), but every compute call fails with :class:`KidError` when no CUDA device is
+usable, and the import itself fails loudly when the shared library has not been built.
+
+Reference seams (``/root/reference/newkmer_10nx.cpp``):
+  Database  <- Hashtable (:158-265) + Tree1 (:93-154)
+  Sample    <- gcount/ucount/kmer_seen globals (:61-64) and main():1017-1043
+  Sample.classify_* <- process_qual (:714-760) + process_read (:452-617)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkmerid_b200.so")
+KSIZE = 30
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make lib` (or __graft_entry__.build()). "
+        "kmer_id_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _u, _sz, _u64 = C.c_void_p, C.c_int, C.c_uint, C.c_size_t, C.c_uint64
+_SIGS = {
+    "kid_last_error": (C.c_char_p, []),
+    "kid_version": (C.c_char_p, []),
+    "kid_device_count": (_i, [C.POINTER(_i)]),
+    "kid_db_build": (_i, [_vp, _vp, _sz, _i, _vp, _i, _i, _u, _i, _vp, C.POINTER(_vp)]),
+    "kid_db_free": (None, [_vp]),
+    "kid_db_n_taxa": (_i, [_vp]),
+    "kid_db_device": (_i, [_vp]),
+    "kid_db_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "kid_db_lookup": (_i, [_vp, _vp, _sz, _vp]),
+    "kid_db_msca": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "kid_db_table_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "kid_sample_create": (_i, [_vp, C.POINTER(_vp)]),
+    "kid_sample_free": (None, [_vp]),
+    "kid_sample_begin": (_i, [_vp, _vp]),
+    "kid_classify_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "kid_classify_host": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "kid_sample_set_chunk_reads": (_i, [_vp, _sz]),
+    "kid_sample_transfer_bytes": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "kid_sample_counts": (_i, [_vp, _vp, _vp, _vp]),
+    "kid_sample_counters": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
+    "kid_sample_gcount_device": (_i, [_vp, C.POINTER(_vp)]),
+    "kid_sample_seen_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "kid_seen_or_device": (_i, [_vp, _vp, C.POINTER(_vp), _i, _u64, _u64, _vp]),
+    "kid_ucount_range_device": (_i, [_vp, _vp, _u64, _u64, _vp, _vp]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(lib, _name)  # AttributeError here = the .so does not match include/kmer_id.h
+    _f.restype = _res
+    _f.argtypes = _args
+
+KID_DB_ACCEPT_U = 1
+ERROR_NAMES = {-1: "KID_EINVAL", -2: "KID_ECUDA", -3: "KID_ENOMEM", -4: "KID_ERANGE",
+               -5: "KID_ETREE", -6: "KID_EFULL"}
+
+
+class KidError(RuntimeError):
+    def __init__(self, code: int):
+        self.code = code
+        msg = lib.kid_last_error().decode("utf-8", "replace")
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise KidError(rc)
+
+
+def device_count() -> int:
+    n = _i(0)
+    rc = lib.kid_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def _np_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _as_ptr(x) -> Optional[int]:
+    """numpy array -> host pointer, torch tensor -> data_ptr(), int -> itself, None -> NULL"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch.Tensor
+
+
+class Database:
+    """GPU-resident probe table + taxonomy (Hashtable + Tree1 of the reference)."""
+
+    def __init__(self, keys, taxa, parent: np.ndarray, device: int = 0, flags: int = 0,
+                 log2_buckets: int = 0, stream: int = 0):
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        on_device = not isinstance(keys, np.ndarray)
+        if on_device:
+            n = int(keys.numel())
+            assert keys.dtype.itemsize == 8 and taxa.dtype.itemsize == 4 and int(taxa.numel()) == n
+        else:
+            keys = np.ascontiguousarray(keys, dtype=np.uint64)
+            taxa = np.ascontiguousarray(taxa, dtype=np.uint32)
+            n = keys.size
+            assert taxa.size == n
+        self._h = _vp()
+        _check(lib.kid_db_build(_as_ptr(keys) if n else None, _as_ptr(taxa) if n else None, n,
+                                int(on_device), _np_ptr(parent), parent.size, device, flags,
+                                log2_buckets, stream or None, C.byref(self._h)))
+        self.n_taxa = parent.size
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.kid_db_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def stats(self) -> dict:
+        a, b, c, d = _u64(), _u64(), _u64(), _u64()
+        _check(lib.kid_db_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"n_distinct": a.value, "n_buckets": b.value, "table_bytes": c.value,
+                "n_displaced": d.value}
+
+    def table_device(self) -> Tuple[int, int]:
+        p, n = _vp(), _u64()
+        _check(lib.kid_db_table_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def lookup(self, keys: np.ndarray) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(keys.size, dtype=np.uint32)
+        _check(lib.kid_db_lookup(self._h, _np_ptr(keys), keys.size, _np_ptr(out)))
+        return out
+
+    def msca(self, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        y = np.ascontiguousarray(y, dtype=np.int32)
+        out = np.zeros(x.size, dtype=np.int32)
+        _check(lib.kid_db_msca(self._h, _np_ptr(x), _np_ptr(y), x.size, _np_ptr(out)))
+        return out
+
+
+class Sample:
+    """Per-sample accumulators (gcount / seen flags -> ucount) and the classify calls."""
+
+    def __init__(self, db: Database):
+        self.db = db
+        self._h = _vp()
+        _check(lib.kid_sample_create(db._h, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.kid_sample_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def begin(self, stream: int = 0):
+        _check(lib.kid_sample_begin(self._h, stream or None))
+
+    def set_chunk_reads(self, n: int):
+        _check(lib.kid_sample_set_chunk_reads(self._h, n))
+
+    def classify_device(self, seq, qual, off, n_reads: int, out_taxon=None, out_span=None,
+                        stream: int = 0):
+        """All arguments are device buffers (torch tensors or raw addresses)."""
+        _check(lib.kid_classify_device(self._h, _as_ptr(seq), _as_ptr(qual), _as_ptr(off), n_reads,
+                                       _as_ptr(out_taxon), _as_ptr(out_span), stream or None))
+
+    def classify_host(self, seq, qual, off, n_reads: int, out_taxon=None, out_span=None):
+        """Host buffers (numpy arrays or pinned torch tensors); returns when outputs are complete."""
+        _check(lib.kid_classify_host(self._h, _as_ptr(seq), _as_ptr(qual), _as_ptr(off), n_reads,
+                                     _as_ptr(out_taxon), _as_ptr(out_span)))
+
+    def classify(self, seq: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray,
+                 want_span: bool = False):
+        """Convenience for tests: numpy in, numpy out."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = off.size - 1
+        if qual is not None:
+            qual = np.ascontiguousarray(qual, dtype=np.uint8)
+            assert qual.size >= int(off[-1])
+        out = np.full(n, -2, dtype=np.int32)
+        span = np.zeros((n, 2), dtype=np.uint32) if want_span else None
+        self.classify_host(seq, qual, off, n, out, span)
+        return (out, span) if want_span else out
+
+    def counts(self, stream: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        g = np.zeros(self.db.n_taxa, dtype=np.int32)
+        u = np.zeros(self.db.n_taxa, dtype=np.int32)
+        _check(lib.kid_sample_counts(self._h, _np_ptr(g), _np_ptr(u), stream or None))
+        return g, u
+
+    def counters(self, stream: int = 0) -> dict:
+        a, b, c = _u64(), _u64(), _u64()
+        _check(lib.kid_sample_counters(self._h, C.byref(a), C.byref(b), C.byref(c), stream or None))
+        return {"lookups": a.value, "hits": b.value, "reads": c.value}
+
+    def transfer_bytes(self) -> Tuple[int, int]:
+        a, b = _u64(), _u64()
+        _check(lib.kid_sample_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def gcount_device(self) -> int:
+        p = _vp()
+        _check(lib.kid_sample_gcount_device(self._h, C.byref(p)))
+        return p.value
+
+    def seen_device(self) -> Tuple[int, int]:
+        p, n = _vp(), _u64()
+        _check(lib.kid_sample_seen_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def seen_or(self, dst: int, srcs, word0: int, n_words: int, stream: int = 0):
+        arr = (_vp * len(srcs))(*srcs)
+        _check(lib.kid_seen_or_device(self.db._h, dst, arr, len(srcs), word0, n_words, stream or None))
+
+    def ucount_range(self, seen: int, word0: int, n_words: int, ucount_partial, stream: int = 0):
+        _check(lib.kid_ucount_range_device(self.db._h, seen, word0, n_words, _as_ptr(ucount_partial),
+                                           stream or None))

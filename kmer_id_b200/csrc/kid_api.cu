@@ -1,0 +1,558 @@
+// kid_api.cu - the C-ABI of include/kmer_id.h: contexts, memory, streams and kernel launches.
+// No CPU fallback: every entry point needs a CUDA device and says so when there is none.
+#include "../../include/kmer_id.h"
+#include "kid_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define KID_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+    } while (0)
+
+struct DeviceGuard { // make `device` current for the call, restore the caller's device after
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct HostSlot { // one half of kid_classify_host's double buffer
+    cudaStream_t stream = nullptr;
+    uint8_t *seq = nullptr, *qual = nullptr;
+    uint64_t *off = nullptr;
+    int32_t *out_taxon = nullptr;
+    uint32_t *out_span = nullptr;
+    size_t cap_bytes = 0, cap_reads = 0;
+};
+
+} // namespace
+
+struct kid_db {
+    int device = 0;
+    int n_taxa = 0;
+    int log2_buckets = 0;
+    int sm_count = 148;
+    unsigned flags = 0;
+    uint64_t n_buckets = 0;
+    uint64_t *slots = nullptr;
+    uint2 *tree = nullptr;
+    uint64_t n_distinct = 0, n_displaced = 0;
+
+    KidTableView table_view() const { return KidTableView{ slots, n_buckets - 1, 60 - log2_buckets }; }
+    KidTreeView tree_view() const { return KidTreeView{ tree, n_taxa }; }
+};
+
+struct kid_sample {
+    const kid_db *db = nullptr;
+    int *gcount = nullptr, *ucount = nullptr;
+    uint32_t *seen = nullptr;
+    uint64_t n_words = 0;
+    unsigned long long *counters = nullptr;
+    cudaEvent_t begin_ev = nullptr;
+    HostSlot slot[2];
+    size_t chunk_reads = (size_t)1 << 18;
+    uint64_t h2d = 0, d2h = 0;
+};
+
+extern "C" {
+
+const char *kid_last_error(void) { return g_err; }
+
+const char *kid_version(void) { return "kmer_id_b200 0.1 (sm_100a)"; }
+
+int kid_device_count(int *n)
+{
+    if (!n) return fail(KID_EINVAL, "kid_device_count: n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(KID_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return KID_OK;
+}
+
+// ------------------------------------------------------------------------------------------ db
+static int build_tree_host(const int32_t *parent, int n_taxa, std::vector<uint2> &node)
+{
+    // Tree1::get_parent (:146-152): nodes 0 and 1 always report the root, whatever parent[] says
+    node.assign((size_t)n_taxa, make_uint2(1u, 0xFFFFFFFFu));
+    for (int v = 0; v < n_taxa; v++) {
+        int pv = (v != 1 && v > 0) ? parent[v] : 1;
+        if (pv < 0 || pv >= n_taxa)
+            return fail(KID_ERANGE, "taxonomy: parent[%d] = %d is outside [0,%d)", v, pv, n_taxa);
+        node[(size_t)v].x = (uint32_t)pv;
+    }
+    node[1].y = 0;
+    std::vector<int> chain;
+    for (int v = 0; v < n_taxa; v++) {
+        if (node[(size_t)v].y != 0xFFFFFFFFu) continue;
+        chain.clear();
+        int w = v;
+        while (node[(size_t)w].y == 0xFFFFFFFFu) {
+            chain.push_back(w);
+            if ((int)chain.size() > n_taxa)
+                return fail(KID_ETREE, "taxonomy: node %d never reaches the root (cycle)", v);
+            w = (int)node[(size_t)w].x;
+        }
+        uint32_t d = node[(size_t)w].y;
+        for (size_t i = chain.size(); i-- > 0;) node[(size_t)chain[i]].y = ++d;
+    }
+    return KID_OK;
+}
+
+int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
+                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_buckets,
+                 void *stream_, kid_db **out)
+{
+    if (!out) return fail(KID_EINVAL, "kid_db_build: out is NULL");
+    *out = nullptr;
+    if (n_taxa < 2 || n_taxa > KID_MAX_TAXA)
+        return fail(KID_EINVAL, "kid_db_build: n_taxa %d outside [2,%d]", n_taxa, KID_MAX_TAXA);
+    if (!parent) return fail(KID_EINVAL, "kid_db_build: parent is NULL");
+    if (n_keys && (!keys || !taxa)) return fail(KID_EINVAL, "kid_db_build: keys/taxa NULL");
+    if (n_keys >= 0xFFFFFFFFull) return fail(KID_EINVAL, "kid_db_build: more than 2^32-2 probe entries");
+    if (log2_buckets && (log2_buckets < KID_MIN_LOG2_BUCKETS || log2_buckets > KID_MAX_LOG2_BUCKETS))
+        return fail(KID_EINVAL, "kid_db_build: log2_buckets %d outside [%d,%d]", log2_buckets,
+                    KID_MIN_LOG2_BUCKETS, KID_MAX_LOG2_BUCKETS);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(KID_ECUDA, "kid_db_build: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(KID_EINVAL, "kid_db_build: device %d of %d", device, ndev);
+
+    std::vector<uint2> node;
+    int rc = build_tree_host(parent, n_taxa, node);
+    if (rc) return rc;
+
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(KID_ECUDA, "cudaSetDevice(%d) failed", device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    const bool fixed = log2_buckets != 0;
+    int B = log2_buckets;
+    if (!fixed) { // about one key per 4-slot bucket: a second sector is needed by ~1 % of lookups
+        B = KID_MIN_LOG2_BUCKETS;
+        while (B < KID_MAX_LOG2_BUCKETS && ((uint64_t)1 << B) < n_keys) B++;
+    }
+
+    kid_db *db = new (std::nothrow) kid_db;
+    if (!db) return fail(KID_ENOMEM, "kid_db_build: host allocation failed");
+    db->device = device;
+    db->n_taxa = n_taxa;
+    db->flags = flags;
+    cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device);
+
+    const uint64_t *dkeys = keys;
+    const uint32_t *dtaxa = taxa;
+    uint64_t *tmp_keys = nullptr;
+    uint32_t *tmp_taxa = nullptr, *owner = nullptr;
+    KidBuildStatus *dstatus = nullptr;
+    auto cleanup_tmp = [&]() {
+        cudaFree(tmp_keys); cudaFree(tmp_taxa); cudaFree(owner); cudaFree(dstatus);
+        tmp_keys = nullptr; tmp_taxa = nullptr; owner = nullptr; dstatus = nullptr;
+    };
+    auto bail = [&](int code) { cleanup_tmp(); kid_db_free(db); return code; };
+#define KID_CUDA_B(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA,            \
+                             "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+
+    KID_CUDA_B(cudaMalloc(&db->tree, sizeof(uint2) * (size_t)n_taxa));
+    KID_CUDA_B(cudaMemcpyAsync(db->tree, node.data(), sizeof(uint2) * (size_t)n_taxa,
+                               cudaMemcpyHostToDevice, stream));
+    if (n_keys && !keys_on_device) {
+        KID_CUDA_B(cudaMalloc(&tmp_keys, sizeof(uint64_t) * n_keys));
+        KID_CUDA_B(cudaMalloc(&tmp_taxa, sizeof(uint32_t) * n_keys));
+        KID_CUDA_B(cudaMemcpyAsync(tmp_keys, keys, sizeof(uint64_t) * n_keys, cudaMemcpyHostToDevice, stream));
+        KID_CUDA_B(cudaMemcpyAsync(tmp_taxa, taxa, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, stream));
+        dkeys = tmp_keys;
+        dtaxa = tmp_taxa;
+    }
+    KID_CUDA_B(cudaMalloc(&dstatus, sizeof(KidBuildStatus)));
+
+    for (;;) {
+        const uint64_t n_buckets = (uint64_t)1 << B;
+        const size_t n_slots = (size_t)(4 * n_buckets);
+        KID_CUDA_B(cudaMalloc(&db->slots, n_slots * sizeof(uint64_t)));
+        KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
+        KID_CUDA_B(cudaMemsetAsync(db->slots, 0, n_slots * sizeof(uint64_t), stream));
+        KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
+        KID_CUDA_B(cudaMemsetAsync(dstatus, 0, sizeof(KidBuildStatus), stream));
+        KID_CUDA_B(kid_launch_build(db->slots, B, owner, dkeys, dtaxa, n_keys, n_taxa, dstatus, stream));
+        KidBuildStatus st;
+        KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
+        KID_CUDA_B(cudaStreamSynchronize(stream));
+        cudaFree(owner);
+        owner = nullptr;
+        if (st.range_error)
+            return bail(fail(KID_ERANGE, "probe table: a probe names a taxon >= n_taxa (%d); the "
+                                         "reference indexes gcount[] out of bounds here", n_taxa));
+        if (!st.overflow) {
+            db->log2_buckets = B;
+            db->n_buckets = n_buckets;
+            db->n_distinct = st.n_distinct;
+            db->n_displaced = st.n_displaced;
+            break;
+        }
+        cudaFree(db->slots);
+        db->slots = nullptr;
+        if (fixed || B == KID_MAX_LOG2_BUCKETS)
+            return bail(fail(KID_EFULL, "probe table: 2^%d buckets cannot place every key", B));
+        B++;
+    }
+    cleanup_tmp();
+    *out = db;
+    return KID_OK;
+#undef KID_CUDA_B
+}
+
+void kid_db_free(kid_db *db)
+{
+    if (!db) return;
+    DeviceGuard guard(db->device);
+    cudaFree(db->slots);
+    cudaFree(db->tree);
+    delete db;
+}
+
+int kid_db_n_taxa(const kid_db *db) { return db ? db->n_taxa : 0; }
+int kid_db_device(const kid_db *db) { return db ? db->device : -1; }
+
+int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets, uint64_t *table_bytes,
+                 uint64_t *n_displaced)
+{
+    if (!db) return fail(KID_EINVAL, "kid_db_stats: db is NULL");
+    if (n_distinct) *n_distinct = db->n_distinct;
+    if (n_buckets) *n_buckets = db->n_buckets;
+    if (table_bytes) *table_bytes = db->n_buckets * 32;
+    if (n_displaced) *n_displaced = db->n_displaced;
+    return KID_OK;
+}
+
+int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_buckets)
+{
+    if (!db || !table) return fail(KID_EINVAL, "kid_db_table_device: NULL argument");
+    *table = db->slots;
+    if (n_buckets) *n_buckets = db->n_buckets;
+    return KID_OK;
+}
+
+int kid_db_lookup(const kid_db *db, const uint64_t *keys, size_t n, uint32_t *taxa_out)
+{
+    if (!db || (n && (!keys || !taxa_out))) return fail(KID_EINVAL, "kid_db_lookup: NULL argument");
+    if (n == 0) return KID_OK;
+    DeviceGuard guard(db->device);
+    uint64_t *dk = nullptr;
+    uint32_t *dt = nullptr;
+    KID_CUDA(cudaMalloc(&dk, n * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&dt, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(dk, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = kid_launch_lookup(db->table_view(), dk, n, dt, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(taxa_out, dt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(dk);
+    cudaFree(dt);
+    if (e != cudaSuccess) return fail(KID_ECUDA, "kid_db_lookup: %s", cudaGetErrorString(e));
+    return KID_OK;
+}
+
+int kid_db_msca(const kid_db *db, const int32_t *x, const int32_t *y, size_t n, int32_t *out)
+{
+    if (!db || (n && (!x || !y || !out))) return fail(KID_EINVAL, "kid_db_msca: NULL argument");
+    for (size_t i = 0; i < n; i++)
+        if (x[i] < 0 || x[i] >= db->n_taxa || y[i] < 0 || y[i] >= db->n_taxa)
+            return fail(KID_ERANGE, "kid_db_msca: pair %zu (%d,%d) outside [0,%d)", i, x[i], y[i], db->n_taxa);
+    if (n == 0) return KID_OK;
+    DeviceGuard guard(db->device);
+    int32_t *d = nullptr;
+    KID_CUDA(cudaMalloc(&d, 3 * n * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(d, x, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, y, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = kid_launch_msca(db->tree_view(), d, d + n, n, d + 2 * n, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(KID_ECUDA, "kid_db_msca: %s", cudaGetErrorString(e));
+    return KID_OK;
+}
+
+// -------------------------------------------------------------------------------------- sample
+int kid_sample_create(const kid_db *db, kid_sample **out)
+{
+    if (!db || !out) return fail(KID_EINVAL, "kid_sample_create: NULL argument");
+    *out = nullptr;
+    DeviceGuard guard(db->device);
+    kid_sample *s = new (std::nothrow) kid_sample;
+    if (!s) return fail(KID_ENOMEM, "kid_sample_create: host allocation failed");
+    s->db = db;
+    const uint64_t n_slots = 4 * db->n_buckets;
+    s->n_words = ((n_slots / 32) + 1023) / 1024 * 1024;
+    cudaError_t e = cudaMalloc(&s->gcount, sizeof(int) * (size_t)db->n_taxa);
+    if (e == cudaSuccess) e = cudaMalloc(&s->ucount, sizeof(int) * (size_t)db->n_taxa);
+    if (e == cudaSuccess) e = cudaMalloc(&s->seen, sizeof(uint32_t) * s->n_words);
+    if (e == cudaSuccess) e = cudaMalloc(&s->counters, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->begin_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        kid_sample_free(s);
+        return fail(e == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA, "kid_sample_create: %s",
+                    cudaGetErrorString(e));
+    }
+    int rc = kid_sample_begin(s, nullptr);
+    if (rc) { kid_sample_free(s); return rc; }
+    KID_CUDA(cudaStreamSynchronize(nullptr));
+    *out = s;
+    return KID_OK;
+}
+
+void kid_sample_free(kid_sample *s)
+{
+    if (!s) return;
+    DeviceGuard guard(s->db->device);
+    for (HostSlot &h : s->slot) {
+        if (h.stream) { cudaStreamSynchronize(h.stream); cudaStreamDestroy(h.stream); }
+        cudaFree(h.seq); cudaFree(h.qual); cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
+    }
+    if (s->begin_ev) cudaEventDestroy(s->begin_ev);
+    cudaFree(s->gcount); cudaFree(s->ucount); cudaFree(s->seen); cudaFree(s->counters);
+    delete s;
+}
+
+int kid_sample_begin(kid_sample *s, void *stream_)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_begin: s is NULL");
+    DeviceGuard guard(s->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    KID_CUDA(cudaMemsetAsync(s->gcount, 0, sizeof(int) * (size_t)s->db->n_taxa, stream));
+    KID_CUDA(cudaMemsetAsync(s->seen, 0, sizeof(uint32_t) * s->n_words, stream));
+    KID_CUDA(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned long long), stream));
+    KID_CUDA(cudaEventRecord(s->begin_ev, stream));
+    s->h2d = s->d2h = 0;
+    return KID_OK;
+}
+
+static KidClassifyParams make_params(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
+                                     const uint64_t *off, uint64_t bias, size_t n, int32_t *out_taxon,
+                                     uint32_t *out_span)
+{
+    KidClassifyParams p;
+    p.table = s->db->table_view();
+    p.tree = s->db->tree_view();
+    p.seq = seq;
+    p.qual = qual;
+    p.off = off;
+    p.off_bias = bias;
+    p.n_reads = n;
+    p.out_taxon = out_taxon;
+    p.out_span = out_span;
+    p.gcount = s->gcount;
+    p.seen = s->seen;
+    p.counters = s->counters;
+    p.accept_u = (s->db->flags & KID_DB_ACCEPT_U) != 0;
+    return p;
+}
+
+int kid_classify_device(kid_sample *s, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                        size_t n_reads, int32_t *out_taxon, uint32_t *out_span, void *stream)
+{
+    if (!s) return fail(KID_EINVAL, "kid_classify_device: s is NULL");
+    if (n_reads == 0) return KID_OK;
+    if (!seq || !off) return fail(KID_EINVAL, "kid_classify_device: seq/off is NULL");
+    DeviceGuard guard(s->db->device);
+    KidClassifyParams p = make_params(s, seq, qual, off, 0, n_reads, out_taxon, out_span);
+    KID_CUDA(kid_launch_classify(p, s->db->sm_count, (cudaStream_t)stream));
+    return KID_OK;
+}
+
+int kid_sample_set_chunk_reads(kid_sample *s, size_t chunk_reads)
+{
+    if (!s || chunk_reads == 0) return fail(KID_EINVAL, "kid_sample_set_chunk_reads: bad argument");
+    s->chunk_reads = chunk_reads;
+    return KID_OK;
+}
+
+int kid_sample_transfer_bytes(const kid_sample *s, uint64_t *h2d, uint64_t *d2h)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_transfer_bytes: s is NULL");
+    if (h2d) *h2d = s->h2d;
+    if (d2h) *d2h = s->d2h;
+    return KID_OK;
+}
+
+static int slot_reserve(HostSlot &h, size_t bytes, size_t reads, bool want_qual)
+{
+    if (!h.stream) KID_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    if (bytes + 64 > h.cap_bytes || (want_qual && !h.qual)) {
+        KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.seq); cudaFree(h.qual);
+        h.seq = h.qual = nullptr;
+        size_t cap = bytes + bytes / 4 + 64;
+        if (cap < h.cap_bytes) cap = h.cap_bytes;
+        h.cap_bytes = 0;
+        KID_CUDA(cudaMalloc(&h.seq, cap));
+        KID_CUDA(cudaMalloc(&h.qual, cap));
+        h.cap_bytes = cap;
+    }
+    if (reads > h.cap_reads) {
+        KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
+        h.off = nullptr; h.out_taxon = nullptr; h.out_span = nullptr;
+        h.cap_reads = 0;
+        const size_t cap = reads + reads / 4 + 16;
+        KID_CUDA(cudaMalloc(&h.off, sizeof(uint64_t) * (cap + 1)));
+        KID_CUDA(cudaMalloc(&h.out_taxon, sizeof(int32_t) * cap));
+        KID_CUDA(cudaMalloc(&h.out_span, sizeof(uint32_t) * 2 * cap));
+        h.cap_reads = cap;
+    }
+    return KID_OK;
+}
+
+int kid_classify_host(kid_sample *s, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                      size_t n_reads, int32_t *out_taxon, uint32_t *out_span)
+{
+    if (!s) return fail(KID_EINVAL, "kid_classify_host: s is NULL");
+    if (n_reads == 0) return KID_OK;
+    if (!seq || !off) return fail(KID_EINVAL, "kid_classify_host: seq/off is NULL");
+    DeviceGuard guard(s->db->device);
+    int k = 0;
+    for (size_t r0 = 0; r0 < n_reads; r0 += s->chunk_reads, k ^= 1) {
+        const size_t n = (n_reads - r0 < s->chunk_reads) ? n_reads - r0 : s->chunk_reads;
+        const uint64_t b0 = off[r0], bytes = off[r0 + n] - b0;
+        HostSlot &h = s->slot[k];
+        int rc = slot_reserve(h, (size_t)bytes, n, qual != nullptr);
+        if (rc) return rc;
+        // the previous chunk on this slot must have drained before its buffers are overwritten
+        // (stream order guarantees it); the very first chunks wait for kid_sample_begin's memsets
+        KID_CUDA(cudaStreamWaitEvent(h.stream, s->begin_ev, 0));
+        KID_CUDA(cudaMemcpyAsync(h.seq, seq + b0, bytes, cudaMemcpyHostToDevice, h.stream));
+        if (qual) KID_CUDA(cudaMemcpyAsync(h.qual, qual + b0, bytes, cudaMemcpyHostToDevice, h.stream));
+        KID_CUDA(cudaMemcpyAsync(h.off, off + r0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h.stream));
+        s->h2d += bytes * (qual ? 2 : 1) + sizeof(uint64_t) * (n + 1);
+        KidClassifyParams p = make_params(s, h.seq, qual ? h.qual : nullptr, h.off, b0, n,
+                                          out_taxon ? h.out_taxon : nullptr,
+                                          out_span ? h.out_span : nullptr);
+        KID_CUDA(kid_launch_classify(p, s->db->sm_count, h.stream));
+        if (out_taxon) {
+            KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
+            s->d2h += sizeof(int32_t) * n;
+        }
+        if (out_span) {
+            KID_CUDA(cudaMemcpyAsync(out_span + 2 * r0, h.out_span, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, h.stream));
+            s->d2h += sizeof(uint32_t) * 2 * n;
+        }
+    }
+    for (HostSlot &h : s->slot)
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+    return KID_OK;
+}
+
+// ---------------------------------------------------------------------------------- sample end
+int kid_sample_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *stream_)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_counts: s is NULL");
+    DeviceGuard guard(s->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t nb = sizeof(int) * (size_t)s->db->n_taxa;
+    if (ucount) {
+        KID_CUDA(cudaMemsetAsync(s->ucount, 0, nb, stream));
+        KID_CUDA(kid_launch_ucount(s->db->slots, s->seen, 0, s->n_words, s->ucount, s->db->n_taxa, stream));
+        KID_CUDA(cudaMemcpyAsync(ucount, s->ucount, nb, cudaMemcpyDeviceToHost, stream));
+    }
+    if (gcount) KID_CUDA(cudaMemcpyAsync(gcount, s->gcount, nb, cudaMemcpyDeviceToHost, stream));
+    KID_CUDA(cudaStreamSynchronize(stream));
+    s->d2h += (gcount ? nb : 0) + (ucount ? nb : 0);
+    return KID_OK;
+}
+
+int kid_sample_counters(kid_sample *s, uint64_t *lookups, uint64_t *hits, uint64_t *reads, void *stream_)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_counters: s is NULL");
+    DeviceGuard guard(s->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long c[2];
+    KID_CUDA(cudaMemcpyAsync(c, s->counters, sizeof c, cudaMemcpyDeviceToHost, stream));
+    if (reads) {
+        std::vector<int> g((size_t)s->db->n_taxa);
+        KID_CUDA(cudaMemcpyAsync(g.data(), s->gcount, sizeof(int) * g.size(), cudaMemcpyDeviceToHost, stream));
+        KID_CUDA(cudaStreamSynchronize(stream));
+        uint64_t t = 0;
+        for (int v : g) t += (uint64_t)v;
+        *reads = t;
+    }
+    KID_CUDA(cudaStreamSynchronize(stream));
+    if (lookups) *lookups = c[0];
+    if (hits) *hits = c[1];
+    return KID_OK;
+}
+
+int kid_sample_gcount_device(kid_sample *s, int32_t **gcount)
+{
+    if (!s || !gcount) return fail(KID_EINVAL, "kid_sample_gcount_device: NULL argument");
+    *gcount = s->gcount;
+    return KID_OK;
+}
+
+int kid_sample_seen_device(kid_sample *s, uint32_t **seen, uint64_t *n_words)
+{
+    if (!s || !seen) return fail(KID_EINVAL, "kid_sample_seen_device: NULL argument");
+    *seen = s->seen;
+    if (n_words) *n_words = s->n_words;
+    return KID_OK;
+}
+
+int kid_seen_or_device(const kid_db *db, uint32_t *dst, const uint32_t *const *src, int n_src,
+                       uint64_t word0, uint64_t n_words, void *stream)
+{
+    if (!db || !dst || !src) return fail(KID_EINVAL, "kid_seen_or_device: NULL argument");
+    if (n_src < 1 || n_src > KID_MAX_OR_SOURCES)
+        return fail(KID_EINVAL, "kid_seen_or_device: n_src %d outside [1,%d]", n_src, KID_MAX_OR_SOURCES);
+    if ((word0 | n_words) & 3 || (reinterpret_cast<uintptr_t>(dst) & 15))
+        return fail(KID_EINVAL, "kid_seen_or_device: ranges must be multiples of 4 words, dst 16-byte aligned");
+    KidPtrList l;
+    for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i < n_src ? src[i] : nullptr;
+    DeviceGuard guard(db->device);
+    KID_CUDA(kid_launch_seen_or(dst, l, n_src, word0, n_words, (cudaStream_t)stream));
+    return KID_OK;
+}
+
+int kid_ucount_range_device(const kid_db *db, const uint32_t *seen, uint64_t word0, uint64_t n_words,
+                            int32_t *ucount_partial, void *stream)
+{
+    if (!db || !seen || !ucount_partial) return fail(KID_EINVAL, "kid_ucount_range_device: NULL argument");
+    if ((word0 | n_words) & 3) return fail(KID_EINVAL, "kid_ucount_range_device: range must be multiples of 4 words");
+    DeviceGuard guard(db->device);
+    KID_CUDA(kid_launch_ucount(db->slots, seen, word0, n_words, ucount_partial, db->n_taxa, (cudaStream_t)stream));
+    return KID_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,106 @@
+// kid_sample.cu - sample-end kernels and the small diagnostic kernels behind the C-ABI.
+//
+// ucount (newkmer_10nx.cpp:596-603) is "number of distinct canonical k-mers hit in this sample,
+// per hit taxon".  Distinct keys are distinct table slots, so it is the per-taxon histogram of
+// the per-slot seen bits - no k-mer set is needed.
+#include "kid_kernels.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+kid_ucount_kernel(const uint64_t *__restrict__ slots, const uint4 *__restrict__ seen4,
+                  uint64_t quad0, uint64_t n_quads, int *ucount, int n_taxa)
+{
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
+         q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(seen4 + quad0 + q);
+        if ((v.x | v.y | v.z | v.w) == 0) continue;
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t bits = w[k];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint64_t slot = ((quad0 + q) * 4 + k) * 32 + b;
+                const uint32_t taxon = (uint32_t)__ldg(slots + slot) & KID_TAXON_MASK;
+                if (taxon < (uint32_t)n_taxa) atomicAdd(ucount + taxon, 1);
+            }
+        }
+    }
+}
+
+// dst[i] = OR over sources of src[k][word0 + i]; sources may be peer-mapped (NVLink) pointers
+__global__ void __launch_bounds__(256)
+kid_seen_or_kernel(uint4 *dst, const KidPtrList src, int n_src, uint64_t quad0, uint64_t n_quads)
+{
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
+         q += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < n_src; k++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(src.p[k])[quad0 + q];
+            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+        }
+        dst[q] = acc;
+    }
+}
+
+__global__ void kid_lookup_kernel(KidTableView t, const uint64_t *keys, size_t n, uint32_t *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t slot;
+        out[i] = kid_lookup_from(t, kid_hash60(keys[i] & KID_MASK60), 0, slot);
+    }
+}
+
+__global__ void kid_msca_kernel(KidTreeView t, const int32_t *x, const int32_t *y, size_t n,
+                                int32_t *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)kid_msca(t, (uint32_t)x[i], (uint32_t)y[i]);
+}
+
+unsigned grid_for(uint64_t n, unsigned threads)
+{
+    uint64_t g = (n + threads - 1) / threads;
+    const uint64_t cap = 148ull * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+} // namespace
+
+cudaError_t kid_launch_ucount(const uint64_t *slots, const uint32_t *seen, uint64_t word0,
+                              uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream)
+{
+    if (n_words == 0) return cudaSuccess;
+    kid_ucount_kernel<<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+        slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_seen_or(uint32_t *dst, const KidPtrList &src, int n_src, uint64_t word0,
+                               uint64_t n_words, cudaStream_t stream)
+{
+    if (n_words == 0) return cudaSuccess;
+    kid_seen_or_kernel<<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+        reinterpret_cast<uint4 *>(dst), src, n_src, word0 / 4, n_words / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_lookup(const KidTableView &t, const uint64_t *keys, size_t n, uint32_t *out,
+                              cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    kid_lookup_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, keys, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_msca(const KidTreeView &t, const int32_t *x, const int32_t *y, size_t n,
+                            int32_t *out, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    kid_msca_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, x, y, n, out);
+    return cudaGetLastError();
+}
