@@ -124,9 +124,9 @@ class Database:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.kid_db_free(self._h)
-            self._h = None
+        self._h = None
 
     __del__ = close
 
@@ -164,9 +164,9 @@ class Sample:
         _check(lib.kid_sample_create(db._h, C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.kid_sample_free(self._h)
-            self._h = None
+        self._h = None
 
     __del__ = close
 

@@ -1,0 +1,203 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact: per-read final taxon, trimmed span, gcount, ucount, lookup and hit counters."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(db, flags=0):
+    from oracle import kor
+    odb = kor.OracleDB(db.n_taxa, flags)
+    odb.set_parents(db.parent)
+    odb.add_keys(db.keys, db.taxa)
+    return odb, kor.OracleSample(odb)
+
+
+def _gpu(db, flags=0, **kw):
+    import kmer_id_b200 as kid
+    gdb = kid.Database(db.keys, db.taxa, db.parent, flags=flags, **kw)
+    return gdb, kid.Sample(gdb)
+
+
+def _check_batch(gs, osamp, batch, with_qual=True):
+    seq, qual = batch.padded()
+    fin_o, span_o = osamp.classify(batch.seq, batch.qual if with_qual else None, batch.off)
+    fin_g, span_g = gs.classify(seq, qual if with_qual else None, batch.off, want_span=True)
+    bad = np.flatnonzero(fin_o != fin_g)
+    assert bad.size == 0, f"{bad.size} reads differ, first {bad[:5]}: oracle {fin_o[bad[:5]]} gpu {fin_g[bad[:5]]}"
+    if with_qual:
+        assert np.array_equal(span_o.astype(np.uint32), span_g)
+    return fin_o
+
+
+def _check_counts(gs, osamp):
+    g, u = gs.counts()
+    assert np.array_equal(g, osamp.gcount)
+    assert np.array_equal(u, osamp.ucount)
+    c = gs.counters()
+    assert c["lookups"] == osamp.lookups
+    assert c["hits"] == osamp.hits
+    assert c["reads"] == osamp.tct
+
+
+def test_lookup_first_wins_and_zero_taxon():
+    rng = np.random.default_rng(7)
+    db = H.make_db(rng, 50000, n_dup=5000, n_zero=400)
+    odb, _ = _oracle(db)
+    gdb, _ = _gpu(db)
+    probe = np.concatenate([db.keys, H.canonical(rng.integers(0, 1 << 60, size=20000, dtype=np.uint64))])
+    want = np.array([odb.lookup(int(k)) for k in probe.tolist()], dtype=np.uint32)
+    got = gdb.lookup(probe)
+    assert np.array_equal(want, got)
+    assert gdb.stats()["n_distinct"] == odb.n_keys
+
+
+def test_msca_exhaustive_sample():
+    rng = np.random.default_rng(8)
+    db = H.make_db(rng, 10)
+    odb, _ = _oracle(db)
+    gdb, _ = _gpu(db)
+    x = rng.integers(1, H.B10_NTAXA, size=20000).astype(np.int32)
+    y = rng.integers(1, H.B10_NTAXA, size=20000).astype(np.int32)
+    # force plenty of related pairs: y = some ancestor of x, or siblings
+    par = db.parent
+    y[:5000] = par[x[:5000]]
+    y[5000:7000] = par[par[x[5000:7000]]]
+    x[7000:8000] = par[y[7000:8000]]
+    y[8000:8500] = x[8000:8500]
+    y[8500:9000] = 1
+    x[9000:9500] = 1
+    want = np.array([odb.msca(int(a), int(b)) for a, b in zip(x, y)], dtype=np.int32)
+    assert np.array_equal(want, gdb.msca(x, y))
+    assert gdb.msca(np.array([37, 35], np.int32), np.array([35, 35], np.int32)).tolist() == [5, 35]
+
+
+@pytest.mark.parametrize("seed,n,kw", [
+    (11, 4000, dict()),
+    (12, 3000, dict(ragged=True)),
+    (13, 3000, dict(lower_rate=0.05, n_rate=0.01)),
+    (14, 2000, dict(length=250, bad_tail=0.6)),
+    (15, 1500, dict(length=31)),
+    (16, 1500, dict(on_target=1.0, sub_rate=0.0, n_rate=0.0)),
+])
+def test_classify_matches_oracle(seed, n, kw):
+    rng = np.random.default_rng(seed)
+    db = H.make_db(rng, 30000, n_dup=500, n_zero=50)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batch = H.make_reads(rng, db, n, **kw)
+    fin = _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
+    if kw.get("length", 150) >= 100:
+        assert (fin > 1).sum() > n // 10, "fixture has too few classified reads"
+    # second batch accumulates into the same sample; a repeat must not bump ucount
+    _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
+    # new sample
+    gs.begin()
+    osamp.reset()
+    b2 = H.make_reads(rng, db, 500, **kw)
+    _check_batch(gs, osamp, b2)
+    _check_counts(gs, osamp)
+
+
+def test_classify_without_quality_fasta_rule():
+    rng = np.random.default_rng(21)
+    db = H.make_db(rng, 20000)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batch = H.make_reads(rng, db, 2500, ragged=True)
+    _check_batch(gs, osamp, batch, with_qual=False)
+    _check_counts(gs, osamp)
+
+
+def test_accept_u_flag():
+    import kmer_id_b200 as kid
+    from oracle import kor
+    rng = np.random.default_rng(22)
+    db = H.make_db(rng, 5000)
+    batch = H.make_reads(rng, db, 1500, sub_rate=0, n_rate=0)
+    batch.seq[batch.seq == ord("T")] = ord("U")
+    batch.seq[::7][batch.seq[::7] == ord("U")] = ord("u")
+    for flags_o, flags_g in ((0, 0), (kor.FLAG_ACCEPT_U, kid.KID_DB_ACCEPT_U)):
+        odb, osamp = _oracle(db, flags_o)
+        gdb, gs = _gpu(db, flags_g)
+        fin = _check_batch(gs, osamp, batch)
+        _check_counts(gs, osamp)
+        assert ((fin > 1).sum() > 100) == bool(flags_o)
+
+
+def test_displaced_entries_small_table_high_load():
+    """Force bucket overflow: 2^22 buckets hold 16.7 M slots; 6 M keys -> many displaced keys."""
+    rng = np.random.default_rng(23)
+    db = H.make_db(rng, 6_000_000)
+    gdb, gs = _gpu(db, log2_buckets=22)
+    st = gdb.stats()
+    assert st["n_displaced"] > 10000
+    odb, osamp = _oracle(db)
+    probe = np.concatenate([db.keys[:200000], H.canonical(rng.integers(0, 1 << 60, size=200000, dtype=np.uint64))])
+    from oracle import kor
+    want = np.zeros(probe.size, np.uint32)
+    for i, k in enumerate(probe.tolist()):
+        want[i] = odb.lookup(k)
+    assert np.array_equal(want, gdb.lookup(probe))
+    batch = H.make_reads(rng, db, 3000)
+    _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
+
+
+def test_device_resident_entry_point_and_chunking():
+    import torch
+    rng = np.random.default_rng(24)
+    db = H.make_db(rng, 20000)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batch = H.make_reads(rng, db, 5000, ragged=True)
+    seq, qual = batch.padded()
+    fin_o, _ = osamp.classify(batch.seq, batch.qual, batch.off)
+    dev = torch.device("cuda:0")
+    dseq = torch.from_numpy(seq).to(dev)
+    dqual = torch.from_numpy(qual).to(dev)
+    doff = torch.from_numpy(batch.off.view(np.int64)).to(dev)
+    dout = torch.full((batch.n,), -7, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gs.begin(stream)
+    gs.classify_device(dseq, dqual, doff, batch.n, dout, None, stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), fin_o)
+    _check_counts(gs, osamp)
+    # host path split into many small chunks must give the same sample totals
+    gs.begin()
+    gs.set_chunk_reads(333)
+    out = gs.classify(seq, qual, batch.off)
+    assert np.array_equal(out, fin_o)
+    _check_counts(gs, osamp)
+
+
+def test_rejects_bad_inputs():
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(25)
+    db = H.make_db(rng, 100)
+    bad_taxa = db.taxa.copy()
+    bad_taxa[5] = H.B10_NTAXA  # gcount[] out of bounds in the reference
+    with pytest.raises(kid.KidError) as e:
+        kid.Database(db.keys, bad_taxa, db.parent)
+    assert e.value.code == -4
+    cyc = db.parent.copy()
+    cyc[100], cyc[101] = 101, 100  # Tree1::msca would never terminate
+    with pytest.raises(kid.KidError) as e:
+        kid.Database(db.keys, db.taxa, cyc)
+    assert e.value.code == -5
+    # empty database and empty batch are fine
+    gdb = kid.Database(np.zeros(0, np.uint64), np.zeros(0, np.uint32), db.parent)
+    gs = kid.Sample(gdb)
+    out = gs.classify(np.zeros(16, np.uint8), np.zeros(16, np.uint8), np.zeros(1, np.uint64))
+    assert out.size == 0
+    b = H.make_reads(rng, db, 50)
+    seq, qual = b.padded()
+    assert (gs.classify(seq, qual, b.off) <= 0).all()
