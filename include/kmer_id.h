@@ -44,6 +44,10 @@ typedef struct kid_sample kid_sample; /* per-sample accumulators: gcount, seen f
 const char *kid_last_error(void);
 int kid_device_count(int *n);
 const char *kid_version(void);
+/* page-locked host memory for the batch buffers handed to kid_classify_host (replaces the
+ * per-line std::string of process_fqgz, newkmer_10nx.cpp:785) */
+int kid_host_alloc(void **p, size_t bytes);
+void kid_host_free(void *p);
 
 /* ---- database ------------------------------------------------------------------------------
  * kid_db_build: replaces Hashtable::Hashtable/add_kmer (newkmer_10nx.cpp:173-180, 235-263) as

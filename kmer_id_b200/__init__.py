@@ -36,6 +36,8 @@ _SIGS = {
     "kid_last_error": (C.c_char_p, []),
     "kid_version": (C.c_char_p, []),
     "kid_device_count": (_i, [C.POINTER(_i)]),
+    "kid_host_alloc": (_i, [C.POINTER(_vp), _sz]),
+    "kid_host_free": (None, [_vp]),
     "kid_db_build": (_i, [_vp, _vp, _sz, _i, _vp, _i, _i, _u, _i, _vp, C.POINTER(_vp)]),
     "kid_db_free": (None, [_vp]),
     "kid_db_n_taxa": (_i, [_vp]),

@@ -102,6 +102,22 @@ int kid_device_count(int *n)
     return KID_OK;
 }
 
+int kid_host_alloc(void **p, size_t bytes)
+{
+    if (!p) return fail(KID_EINVAL, "kid_host_alloc: p is NULL");
+    *p = nullptr;
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA, "cudaHostAlloc(%zu): %s", bytes,
+                    cudaGetErrorString(e));
+    return KID_OK;
+}
+
+void kid_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------------ db
 static int build_tree_host(const int32_t *parent, int n_taxa, std::vector<uint2> &node)
 {

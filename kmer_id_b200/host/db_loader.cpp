@@ -1,0 +1,200 @@
+#include "db_loader.hpp"
+#include "gz_lines.hpp"
+
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <thread>
+
+namespace kidhost {
+
+bool load_tree(const std::string &path, int n_taxa, std::vector<int32_t> &parent, std::string &msg)
+{
+    parent.assign((size_t)n_taxa, 1); // Tree1(): every node hangs off the root
+    std::ifstream fin(path);
+    if (!fin) return true; // the reference prints "tree loaded" regardless (:974-984)
+    std::string line;
+    int i = 0, j = 0; // carried across lines when an extraction fails, like the reference's locals
+    while (std::getline(fin, line)) {
+        std::stringstream ls(line);
+        ls >> i >> j;
+        if (i < 0 || i >= n_taxa || j < 0 || j >= n_taxa) {
+            msg = "taxonomy edge " + std::to_string(i) + " " + std::to_string(j) +
+                  " is outside [0," + std::to_string(n_taxa) + ")";
+            return false;
+        }
+        parent[(size_t)j] = i;
+    }
+    return true;
+}
+
+static inline bool is_ws(unsigned char c)
+{
+    return c == ' ' || (c >= '\t' && c <= '\r');
+}
+
+// process_kmer (:619-661): forward strand, upper-case ACGT only, every full 30-window
+static inline void add_windows(const char *s, size_t n, uint32_t target, std::vector<uint64_t> &keys,
+                               std::vector<uint32_t> &taxa)
+{
+    const uint64_t mask = (1ULL << 60) - 1;
+    uint64_t kf = 0;
+    int cpos = 0;
+    for (size_t i = 0; i < n; i++) {
+        unsigned c;
+        switch (s[i]) {
+        case 'A': c = 0; break;
+        case 'C': c = 1; break;
+        case 'G': c = 2; break;
+        case 'T': c = 3; break;
+        default: cpos = 0; kf = 0; continue;
+        }
+        kf = ((kf << 2) & mask) | c;
+        if (++cpos == 30) {
+            keys.push_back(kf);
+            taxa.push_back(target);
+            cpos--;
+        }
+    }
+}
+
+// digits only, 1..9 of them (cannot overflow an int); anything else sends the line to the slow path
+static inline bool fast_uint(const char *&p, const char *end, uint32_t &v)
+{
+    const char *q = p;
+    uint32_t x = 0;
+    while (q < end && *q >= '0' && *q <= '9' && q - p < 10) x = x * 10 + (uint32_t)(*q++ - '0');
+    if (q == p || q - p > 9) return false;
+    v = x;
+    p = q;
+    return true;
+}
+
+bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
+                      std::vector<uint32_t> &taxa)
+{
+    if (len > 0 && line[len - 1] == '\r') len--; // :691-692
+    if (len == 0) return false;                   // :693
+    const char *p = line, *end = line + len;
+    // fast path: SEQ,uint,uint,uint,char,uint  - the format the builder writes
+    {
+        const char *s0 = p;
+        while (p < end && *p != ',' && !is_ws((unsigned char)*p)) p++;
+        const size_t slen = (size_t)(p - s0);
+        uint32_t target, org, pos, count;
+        if (slen > 0 && p < end && *p == ',' && (++p, fast_uint(p, end, target)) && p < end && *p == ',' &&
+            (++p, fast_uint(p, end, org)) && p < end && *p == ',' && (++p, fast_uint(p, end, pos)) &&
+            p < end && *p == ',' && p + 2 < end && p[1] != ',' && !is_ws((unsigned char)p[1]) &&
+            p[2] == ',' && (p += 3, fast_uint(p, end, count))) {
+            add_windows(s0, slen, target, keys, taxa);
+            return true;
+        }
+    }
+    // slow path: the reference's own extraction sequence on the comma->blank line (:695-697)
+    std::string l(line, len);
+    std::replace(l.begin(), l.end(), ',', ' ');
+    std::istringstream ss(l);
+    std::string sequence;
+    unsigned int target;
+    int org, position, count;
+    char strand;
+    if (ss >> sequence >> target >> org >> position >> strand >> count) {
+        add_windows(sequence.data(), sequence.size(), target, keys, taxa);
+        return true;
+    }
+    return false;
+}
+
+namespace {
+struct Block {
+    std::vector<char> text;
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> taxa;
+    long long lines = 0;
+    bool done = false;
+};
+} // namespace
+
+void load_probes_gz(const std::string &path, ProbeSet &out, unsigned threads)
+{
+    if (threads == 0) threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    GzLineBlocks src(path);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::shared_ptr<Block>> todo, inorder;
+    bool eof = false;
+
+    auto worker = [&] {
+        for (;;) {
+            std::shared_ptr<Block> b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !todo.empty() || eof; });
+                if (todo.empty()) return;
+                b = todo.front();
+                todo.pop_front();
+            }
+            const char *p = b->text.data(), *end = p + b->text.size();
+            b->keys.reserve(b->text.size() / 48);
+            b->taxa.reserve(b->text.size() / 48);
+            while (p < end) {
+                const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+                if (!eol) break;
+                b->lines += parse_probe_line(p, (size_t)(eol - p), b->keys, b->taxa);
+                p = eol + 1;
+            }
+            std::vector<char>().swap(b->text);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                b->done = true;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(worker);
+
+    auto drain = [&](bool all) { // append finished blocks in file order
+        for (;;) {
+            std::shared_ptr<Block> b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (inorder.empty()) return;
+                if (all) cv.wait(lk, [&] { return inorder.front()->done; });
+                if (!inorder.front()->done) return;
+                b = inorder.front();
+                inorder.pop_front();
+            }
+            out.keys.insert(out.keys.end(), b->keys.begin(), b->keys.end());
+            out.taxa.insert(out.taxa.end(), b->taxa.begin(), b->taxa.end());
+            out.lines_parsed += b->lines;
+        }
+    };
+
+    std::vector<char> text;
+    while (src.next(text)) {
+        auto b = std::make_shared<Block>();
+        b->text.swap(text);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return todo.size() < 4 * threads; });
+            todo.push_back(b);
+            inorder.push_back(b);
+        }
+        cv.notify_all();
+        drain(false);
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        eof = true;
+    }
+    cv.notify_all();
+    drain(true);
+    for (auto &t : pool) t.join();
+}
+
+} // namespace kidhost

@@ -1,0 +1,167 @@
+// nk10 - GPU drop-in for the reference's `./nk10 <dir/>` (newkmer_10nx.cpp main():915-1054).
+//
+// Same contract: run from a directory that holds ./bact10/{bData10.txt,btree_10.txt,
+// probes10.txt.gz}; argv[1] is the FASTQ directory WITH its trailing slash; for every
+// <s>_R1_tr.fastq.gz in it (readdir order) classify R1 then R2 and write <dir><s>_result.txt and
+// <dir><s>_reads.txt; same stdout progress lines.  The per-read work happens in
+// libkmerid_b200.so (include/kmer_id.h); there is no CPU classification path in this program.
+//
+// Extras that do not change the contract: KID_DEVICE=<n> picks the GPU, KID_STATS=1 prints phase
+// timings to stderr.
+#include "../../include/kmer_id.h"
+#include "db_loader.hpp"
+#include "fastq_reader.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+using namespace kidhost;
+
+namespace {
+const int MAXTAR = 5982;                    // newkmer_10nx.cpp:45
+const int SAVENUM = 12;                     // :48
+const std::string e1 = "_R1_tr.fastq.gz";   // :29
+const std::string e2 = "_R2_tr.fastq.gz";   // :30
+const std::string iname = "./bact10/bData10.txt";      // :67
+const std::string pname = "./bact10/probes10.txt.gz";  // :68
+const std::string tname = "./bact10/btree_10.txt";     // :69
+
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+[[noreturn]] void die(int code, const std::string &msg)
+{
+    std::cerr << "nk10: " << msg << std::endl;
+    exit(code);
+}
+
+struct SampleState {
+    std::vector<int> gcount_host; // running copy, only to decide the first SAVENUM reads per taxon
+    long long tct = 0;
+};
+
+// classify one FASTQ file batch by batch; appends to _reads.txt exactly as process_read :608-614
+void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream &outread)
+{
+    FastqBatchReader reader(path, (size_t)1 << 19, (size_t)96 << 20);
+    std::vector<int32_t> taxon;
+    std::vector<uint32_t> span;
+    for (;;) {
+        ReadBatch *b = reader.next();
+        if (b->n) {
+            taxon.resize(b->n);
+            span.resize(2 * b->n);
+            if (kid_classify_host(smp, b->seq, b->qual, b->off.data(), b->n, taxon.data(), span.data()) != 0)
+                die(1, kid_last_error());
+            for (size_t r = 0; r < b->n; r++) {
+                const int fin = taxon[r];
+                if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
+                if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) {
+                    outread << ">" << fin << ":";
+                    outread.write(b->names.data() + b->name_off[r], b->name_off[r + 1] - b->name_off[r]);
+                    outread << std::endl;
+                    outread.write((const char *)b->seq + b->off[r] + span[2 * r], span[2 * r + 1] - span[2 * r] + 1);
+                    outread << std::endl;
+                }
+                st.gcount_host[(size_t)fin]++;
+                st.tct++;
+            }
+        }
+        const bool last = b->last;
+        reader.recycle(b);
+        if (last) break;
+    }
+}
+} // namespace
+
+int main(int argc, char *argv[])
+{
+    const bool stats = getenv("KID_STATS") != nullptr;
+    const int device = getenv("KID_DEVICE") ? atoi(getenv("KID_DEVICE")) : 0;
+    std::string dname = argc > 1 ? argv[1] : "/mnt/dmb/Mark_backup/J/"; // :933-942
+    const double t0 = now();
+
+    // strain list: only feeds the (dead) alignment branch, but its absence is reported (:951-971)
+    {
+        std::ifstream fin(iname);
+        if (!fin) std::cout << "narin " << iname << std::endl;
+    }
+    std::vector<int32_t> parent;
+    std::string msg;
+    if (!load_tree(tname, MAXTAR, parent, msg)) die(1, msg);
+    std::cout << "tree loaded" << std::endl; // :984
+
+    ProbeSet probes;
+    load_probes_gz(pname, probes);
+    const double t1 = now();
+    kid_db *db = nullptr;
+    if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), MAXTAR,
+                     device, 0, 0, nullptr, &db) != 0) {
+        if (std::string(kid_last_error()).find("cannot place") != std::string::npos) {
+            std::cout << "out of memory in table " << std::endl; // :258-259
+            exit(1);
+        }
+        die(1, kid_last_error());
+    }
+    std::cout << probes.lines_parsed << " kmers loaded" << std::endl; // :989
+    { ProbeSet().keys.swap(probes.keys); std::vector<uint32_t>().swap(probes.taxa); }
+    const double t2 = now();
+
+    // all samples in the directory, readdir order (:992-1014)
+    std::vector<std::string> fnames;
+    std::cout << dname << std::endl;
+    if (DIR *dir = opendir(dname.c_str())) {
+        while (struct dirent *ent = readdir(dir)) {
+            const std::string name1 = ent->d_name;
+            const size_t pos = name1.find(e1);
+            if (pos != std::string::npos) fnames.push_back(name1.substr(0, pos));
+        }
+        closedir(dir);
+    } else {
+        std::cout << "hosed" << std::endl;
+        perror("");
+        return EXIT_FAILURE;
+    }
+
+    kid_sample *smp = nullptr;
+    if (kid_sample_create(db, &smp) != 0) die(1, kid_last_error());
+    std::vector<int32_t> gcount((size_t)MAXTAR), ucount((size_t)MAXTAR);
+    for (const std::string &s : fnames) {
+        const double ts = now();
+        if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error()); // :1017-1019
+        SampleState st;
+        st.gcount_host.assign((size_t)MAXTAR, 0);
+        const std::string oname2 = dname + s + "_result.txt", trname = dname + s + "_reads.txt";
+        std::cout << s << std::endl; // :1022
+        std::ofstream outread(trname.c_str(), std::ofstream::out | std::ofstream::trunc);
+        run_file(smp, dname + s + e1, st, outread);
+        std::cout << st.tct << " reads loaded" << std::endl; // :1030
+        run_file(smp, dname + s + e2, st, outread);
+        std::cout << st.tct << " reads loaded" << std::endl; // :1036
+        outread.close();
+        if (kid_sample_counts(smp, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
+        std::ofstream out2(oname2);
+        for (int i = 0; i < MAXTAR; i++) out2 << i << "," << gcount[(size_t)i] << "," << ucount[(size_t)i] << "\n";
+        out2.close();
+        if (stats) {
+            uint64_t lk = 0, hits = 0, rd = 0;
+            kid_sample_counters(smp, &lk, &hits, &rd, nullptr);
+            fprintf(stderr, "[nk10] %s: %lld reads, %llu lookups, %llu hits in %.3f s\n", s.c_str(), st.tct,
+                    (unsigned long long)lk, (unsigned long long)hits, now() - ts);
+        }
+    }
+    if (stats)
+        fprintf(stderr, "[nk10] parse db %.3f s, build table %.3f s, total %.3f s\n", t1 - t0, t2 - t1, now() - t0);
+    kid_sample_free(smp);
+    kid_db_free(db);
+    return 0;
+}

@@ -1,0 +1,90 @@
+"""The C++ host `nk10` (kmer_id_b200/bin/nk10) against the compiled reference on the same files:
+stdout lines, <sample>_result.txt and <sample>_reads.txt must be byte-identical.  A byte-identical
+_result.txt implies an identical readbatch_10.py CSV (it is a pure function of that file and
+refkey10.txt, readbatch_10.py:23-138)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+NK_GPU = os.path.join(H.ROOT, "kmer_id_b200", "bin", "nk10")
+NK_REF = H.ref_binary("nk10_small")
+SYNTH = os.path.join(H.ROOT, "tools", "kid_synth")
+
+
+def _run_both(work, fq):
+    r_ref = H.run_nk10(NK_REF, work, fq)
+    assert r_ref.returncode == 0, r_ref.stderr
+    ref_files = {}
+    for f in sorted(os.listdir(fq)):
+        if f.endswith(("_result.txt", "_reads.txt")):
+            p = os.path.join(fq, f)
+            ref_files[f] = open(p, "rb").read()
+            os.remove(p)
+    r_gpu = H.run_nk10(NK_GPU, work, fq)
+    assert r_gpu.returncode == 0, r_gpu.stderr.decode()
+    assert r_gpu.stdout == r_ref.stdout
+    assert ref_files
+    for f, want in ref_files.items():
+        got = open(os.path.join(fq, f), "rb").read()
+        assert got == want, f"{f} differs from the reference's"
+    return ref_files
+
+
+@pytest.mark.skipif(NK_REF is None, reason="oracle/_ref/nk10_small not built")
+def test_config0_synthetic_100k_pairs(tmp_path):
+    """BASELINE.json configs[0]: 1/100-scale synthetic bact10 DB + 100 k synthetic 150-bp pairs."""
+    work = str(tmp_path)
+    fq = os.path.join(work, "fq")
+    g = os.path.join(H.GOLDEN, "b10")
+    subprocess.run([SYNTH, "db", "--golden", g, "--out", work, "--den", "100"], check=True)
+    subprocess.run([SYNTH, "reads", "--golden", g, "--out", fq, "--sample", "cfg0", "--pairs", "100000",
+                    "--den", "100"], check=True)
+    files = _run_both(work, fq)
+    res = files["cfg0_result.txt"].decode().split("\n")
+    assert len(res) == H.B10_NTAXA + 1
+    g_, u_ = H.read_result(os.path.join(fq, "cfg0_result.txt"))
+    assert g_.sum() == 200000 and g_[0] < 80000 and u_.sum() > 100000
+
+
+@pytest.mark.skipif(NK_REF is None, reason="oracle/_ref/nk10_small not built")
+def test_parser_quirks_two_samples(tmp_path):
+    rng = np.random.default_rng(3003)
+    db = H.make_db(rng, 5000, n_dup=200, n_zero=40)
+    work = str(tmp_path)
+    fq = os.path.join(work, "fq")
+    os.makedirs(fq)
+    extra = [
+        b"acgtacgtacgtacgtacgtacgtacgtac,7,0,0,F,1\n",
+        b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT,9,1,2,F,1\n",
+        b"ACGTACGTACGTNCGTACGTACGTACGTACGTACGTACGTAAAAAAAAAAAAAAAAAAAAAAAAAA,11,1,2,R,1\n",
+        b"GGGGGGGGGGGGGGGGGGGGGGGGGGGGGG,12,1,2,F\n",
+        b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTT,13,1,x,F,1\n",
+        b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCA 14 1 2 F 1\r\n",
+        b"\n",
+        b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCG,15,1,2,F1\n",
+        b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCT,16,1,2,F,1,extra,fields\n",
+        b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCAA,00017,+1,-2,F,1\n",
+        b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAC,18,1,2,F,1",
+    ]
+    H.make_bact10_dir(work, db, extra_lines=extra)
+    a = H.make_reads(rng, db, 1200, lower_rate=0.01)
+    b = H.make_reads(rng, db, 1200, ragged=True, name_prefix="T")
+    # reads made of the hand-written probes so that those lines matter
+    special = [b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT", b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCANNCCCCCCCCCCCCCCCCCCCCCCCCCCCCCG",
+               b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCTACCCCCCCCCCCCCCCCCCCCCCCCCCCCCCAA",
+               b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAACGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG"]
+    seq = np.frombuffer(b"".join(special), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in special])]).astype(np.uint64)
+    c = H.ReadBatch(seq=seq, qual=np.full(seq.size, ord("I"), np.uint8), off=off,
+                    names=[b"@sp%d" % i for i in range(len(special))])
+    H.write_fastq_gz(os.path.join(fq, "sampA_R1_tr.fastq.gz"), a, members=3)
+    H.write_fastq_gz(os.path.join(fq, "sampA_R2_tr.fastq.gz"), b, crlf=True)
+    H.write_fastq_gz(os.path.join(fq, "sampB_R1_tr.fastq.gz"), b, final_newline=False)
+    H.write_fastq_gz(os.path.join(fq, "sampB_R2_tr.fastq.gz"), c)
+    _run_both(work, fq)
