@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py - the nk10 read-classification hot path on B200, one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W              (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path)
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): synthetic bact10-scale
+probe database (108 585 519 probes = sum of the shipped refkey10.txt counts, b10 taxonomy) and
+10 M synthetic 150-bp read pairs per GPU (tools/synth/kid_synth.h).  A *step* is one whole sample:
+kid_sample_begin -> classify every read of the batch -> sample end (ucount histogram, counts to
+the host; for N > 1 the cross-rank gcount sum / seen-bitmap OR).  A pair is two independently
+classified reads.
+
+  value  pairs/s with the batch already resident in HBM (CUDA events on the launching stream)
+  e2e    the same through kid_classify_host from pinned HOST buffers (H2D + D2H inside the region)
+  roofline.achieved = lookups/launch x 32 B / mean classify-kernel time  (32 B = one DRAM sector per
+           lookup); peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the CPU oracle (a port, oracle/kid_oracle.c) single-threaded on a bounded sample
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN_B10 = os.path.join(ROOT, "tests", "golden", "b10")
+METRIC = "paired_reads_per_sec_classified"
+UNIT = "pairs/s"
+READ_LEN = 150
+SECTOR_BYTES = 32
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU per step")
+    ap.add_argument("--db-den", type=int, default=1, help="probe DB = refkey counts / den")
+    ap.add_argument("--cpu-baseline-reads", type=int, default=400_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=80.0,
+                    help="CPU seconds the reference arm may spend classifying (all steps together)")
+    return ap.parse_args()
+
+
+def workload_config(args, n_probes):
+    return {
+        "workload": "BASELINE.json configs[2]: bact10-scale synthetic probe DB + 10M synthetic 150bp pairs per GPU",
+        "db_probes": int(n_probes),
+        "db": "b10 taxonomy, refkey10 probe counts / %d, random canonical 30-mers (seed 10)" % args.db_den,
+        "pairs_per_gpu_per_step": args.pairs,
+        "read_len": READ_LEN,
+        "reads": "70% stitched from lineage probes, 0.5% subs, 0.1% N, 20% low-quality tails (seed 21)",
+        "sharding": "reads sharded across ranks, table replicated",
+        "l2": "inputs_larger_than_l2 (%.1f GB of reads + %.1f GB table per step)"
+              % (args.pairs * 2 * READ_LEN * 2 / 1e9, 4.3 / max(1, args.db_den)),
+    }
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while a timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or \
+               [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 3 + i and r[3 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_lookup():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import kmer_id_b200 as kid  # raises if the CUDA library is not built: no fallback
+    from kmer_id_b200 import multi_gpu
+    from tools import synthlib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    parent, prefix = synthlib.load_taxonomy(GOLDEN_B10, 1, args.db_den)
+    wl = synthlib.Workload(parent, prefix, read_len=READ_LEN)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- database: generated on the device, built by the library's own kernels
+    launches0 = kid.kernel_launches()
+    dk = torch.empty(wl.n_probes, dtype=torch.int64, device=dev)
+    dt = torch.empty(wl.n_probes, dtype=torch.int32, device=dev)
+    wl.db_device(local, dk, dt, stream=stream)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    db = kid.Database(dk, dt, parent, device=local, stream=stream)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    st = db.stats()
+
+    # ---- this rank's reads, resident in HBM
+    n_reads = 2 * args.pairs
+    nbytes = n_reads * READ_LEN
+    dseq = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+    dqual = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+    wl.reads_device(local, rank * n_reads, n_reads, dseq, dqual, stream=stream)
+    doff = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * READ_LEN
+    dout = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    sample = kid.Sample(db)
+    engine = multi_gpu.CudaEngine(sample, stream)
+    torch.cuda.synchronize()
+
+    k_ev = []
+
+    def step_device(timed: bool):
+        sample.begin(stream)
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        sample.classify_device(dseq, dqual, doff, n_reads, dout, None, stream)
+        if timed:
+            b.record()
+            k_ev.append((a, b))
+        return multi_gpu.sample_end(engine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        gcount, ucount = step_device(False)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    l_before = kid.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        gcount, ucount = step_device(True)
+    e1.record()
+    barrier()
+    tc1 = time.perf_counter()
+    gpu_launches = kid.kernel_launches() - l_before
+    ms = e0.elapsed_time(e1)
+    counters = sample.counters(stream)  # of the last step
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * args.pairs / (ms_per_step / 1e3)
+    if world == 1:
+        assert int(gcount.sum()) == counters["reads"], "gcount does not add up to the reads classified"
+
+    # ---- end to end through the host-buffer entry point
+    e2e = None
+    if not args.no_e2e:
+        hseq = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+        hqual = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+        hseq.copy_(dseq)
+        hqual.copy_(dqual)
+        hoff = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN))
+        hout = torch.empty(n_reads, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def step_e2e():
+            sample.begin(stream)
+            sample.classify_host(hseq, hqual, hoff, n_reads, hout, None)
+            return multi_gpu.sample_end(engine)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            g2, u2 = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g2, u2 = step_e2e()
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_e2e = float(t.item())
+        h2d, d2h = sample.transfer_bytes()
+        assert np.array_equal(g2, gcount) and np.array_equal(u2, ucount), "host and device paths disagree"
+        assert np.array_equal(hout.numpy(), dout.cpu().numpy())
+        e2e = {"value": world * args.pairs * args.steps / dt_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 8 * db.n_taxa),
+               "ms_per_step": dt_e2e / args.steps * 1e3}
+    clk = clocks.stop(tc0, None)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    lookups = counters["lookups"]
+    peak, peak_src = measured_peak()
+    achieved = lookups * SECTOR_BYTES / (kernel_ms / 1e3) / 1e9
+    tr = traffic_per_lookup()
+    roofline = {"bound": "hbm", "kernel": "kid_classify_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (tr["dram_bytes_per_lookup"] * lookups if tr else None),
+                "algorithmic_bytes_per_lookup": SECTOR_BYTES, "lookups_per_launch": lookups,
+                "kernel_ms": kernel_ms, "lookups_per_s": lookups / (kernel_ms / 1e3),
+                "random_sector_gather_ceiling_gsectors_s": (tr or {}).get("gather_ceiling_gsectors_s")}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
+        "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e,
+        "gpu_launches": int(gpu_launches), "roofline": roofline,
+        "lookups_per_s_whole_step": world * lookups / (ms_per_step / 1e3),
+        "table": {"bytes": st["table_bytes"], "distinct_keys": st["n_distinct"], "displaced": st["n_displaced"],
+                  "build_s": build_s},
+        "hit_fraction": counters["hits"] / max(1, lookups),
+        "classified_fraction": float((gcount[2:].sum()) / max(1, gcount.sum())),
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_port(args, wl, dk, dt, parent, gcount_check=None)
+    del dk, dt
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_port(args, wl, dk, dt, parent, gcount_check):
+    """The CPU oracle (kind = "port"), one thread, on the first cpu_baseline_reads reads of the same
+    workload against the FULL probe table (so its cache behaviour is the real one)."""
+    import numpy as np
+    from oracle import kor
+    n = min(args.cpu_baseline_reads, 2 * args.pairs)
+    keys = dk.cpu().numpy().view(np.uint64)
+    taxa = dt.cpu().numpy().view(np.uint32)
+    odb = kor.OracleDB(wl.n_taxa)
+    odb.set_parents(parent)
+    odb.add_keys(keys, taxa)
+    seq, qual = wl.reads_host(0, n)
+    off = wl.offsets(n)
+    osamp = kor.OracleSample(odb)
+    t0 = time.perf_counter()
+    osamp.classify(seq, qual, off)
+    dt_s = time.perf_counter() - t0
+    return {"value": (n / 2) / dt_s, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d reads of rank 0's batch, full %d-probe table, oracle/kid_oracle.c" % (n, keys.size),
+            "lookups_per_s": osamp.lookups / dt_s, "seconds": dt_s}
+
+
+# ------------------------------------------------------------------------------------ reference
+def run_reference(args):
+    """The reference's own CPU implementation: oracle/_ref/nk10 (unmodified newkmer_10nx.cpp,
+    single-threaded - it has no threading) on a bounded sample of the workload: a 1/100-scale probe
+    DB in its own text format and (warmup+steps) samples of P pairs each, one nk10 process; a step is
+    one sample, timed from its name line to its second "reads loaded" line on stdout."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import tempfile
+    nk10 = os.path.join(ROOT, "oracle", "_ref", "nk10")
+    synth = os.path.join(ROOT, "tools", "kid_synth")
+    n_samples = args.warmup + args.steps
+    if not (os.path.exists(nk10) and os.path.exists(synth)):
+        return run_reference_port(args)
+    pairs = max(2000, int(args.ref_seconds * 16000 / max(1, n_samples)))  # ~32 k reads/s single thread
+    den = 100
+    work = tempfile.mkdtemp(prefix="kid_ref_")
+    fq = os.path.join(work, "fq")
+    subprocess.run([synth, "db", "--golden", GOLDEN_B10, "--out", work, "--den", str(den)], check=True,
+                   stdout=subprocess.DEVNULL)
+    for i in range(n_samples):
+        subprocess.run([synth, "reads", "--golden", GOLDEN_B10, "--out", fq, "--sample", "s%03d" % i,
+                        "--pairs", str(pairs), "--first-pair", str(i * pairs), "--den", str(den)], check=True,
+                       stdout=subprocess.DEVNULL)
+    proc = subprocess.Popen([nk10, fq + "/"], cwd=work, stdout=subprocess.PIPE, text=True)
+    stamps = []
+    for line in proc.stdout:
+        stamps.append((time.perf_counter(), line.rstrip("\n")))
+    proc.wait()
+    if proc.returncode != 0:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/nk10 exited %d" % proc.returncode}))
+        return
+    steps = []
+    i = 0
+    while i < len(stamps):
+        t, text = stamps[i]
+        if text.startswith("s") and len(text) == 4 and text[1:].isdigit():
+            # name line, "<n> reads loaded", "<n> reads loaded"
+            t_end, last = stamps[i + 2]
+            steps.append((t_end - t, int(last.split()[0])))
+            i += 3
+        else:
+            i += 1
+    timed = steps[args.warmup:] if len(steps) > args.warmup else steps
+    sec = statistics.mean(s for s, _ in timed)
+    value = pairs / sec
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    cfg = workload_config(args, 108_585_519)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
+           "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                            "sample": "unmodified nk10 (g++ -O3), 1 thread; probe DB sampled 1/%d (%s lines of text) in "
+                                      "its 2^30-cell table, %d pairs per step, %d steps in one process"
+                                      % (den, "1083547", pairs, n_samples)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_reference_port(args):
+    """Fallback when oracle/_ref/nk10 is absent: the in-repo CPU port, one thread."""
+    import numpy as np
+    from oracle import kor
+    from tools import synthlib
+    parent, prefix = synthlib.load_taxonomy(GOLDEN_B10, 1, 100)
+    wl = synthlib.Workload(parent, prefix, read_len=READ_LEN)
+    keys, taxa = wl.db_host()
+    odb = kor.OracleDB(wl.n_taxa)
+    odb.set_parents(parent)
+    odb.add_keys(keys, taxa)
+    n_samples = args.warmup + args.steps
+    pairs = max(2000, int(args.ref_seconds * 30000 / max(1, n_samples)))
+    osamp = kor.OracleSample(odb)
+    secs = []
+    for i in range(n_samples):
+        seq, qual = wl.reads_host(2 * i * pairs, 2 * pairs)
+        off = wl.offsets(2 * pairs)
+        osamp.reset()
+        t0 = time.perf_counter()
+        osamp.classify(seq, qual, off)
+        secs.append(time.perf_counter() - t0)
+    sec = statistics.mean(secs[args.warmup:])
+    value = pairs / sec
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
+           "config": workload_config(args, 108_585_519),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "oracle/kid_oracle.c, 1/100 probe DB, %d pairs per step" % pairs},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

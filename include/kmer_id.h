@@ -44,6 +44,8 @@ typedef struct kid_sample kid_sample; /* per-sample accumulators: gcount, seen f
 const char *kid_last_error(void);
 int kid_device_count(int *n);
 const char *kid_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+unsigned long long kid_kernel_launches(void);
 /* page-locked host memory for the batch buffers handed to kid_classify_host (replaces the
  * per-line std::string of process_fqgz, newkmer_10nx.cpp:785) */
 int kid_host_alloc(void **p, size_t bytes);

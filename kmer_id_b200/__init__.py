@@ -36,6 +36,7 @@ _SIGS = {
     "kid_last_error": (C.c_char_p, []),
     "kid_version": (C.c_char_p, []),
     "kid_device_count": (_i, [C.POINTER(_i)]),
+    "kid_kernel_launches": (C.c_ulonglong, []),
     "kid_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "kid_host_free": (None, [_vp]),
     "kid_db_build": (_i, [_vp, _vp, _sz, _i, _vp, _i, _i, _u, _i, _vp, C.POINTER(_vp)]),
@@ -86,6 +87,10 @@ def device_count() -> int:
     n = _i(0)
     rc = lib.kid_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def kernel_launches() -> int:
+    return int(lib.kid_kernel_launches())
 
 
 def _np_ptr(a: np.ndarray) -> int:

@@ -10,6 +10,8 @@
 #include <new>
 #include <vector>
 
+unsigned long long g_kid_kernel_launches = 0;
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -100,6 +102,11 @@ int kid_device_count(int *n)
     }
     *n = c;
     return KID_OK;
+}
+
+unsigned long long kid_kernel_launches(void)
+{
+    return __atomic_load_n(&g_kid_kernel_launches, __ATOMIC_RELAXED);
 }
 
 int kid_host_alloc(void **p, size_t bytes)

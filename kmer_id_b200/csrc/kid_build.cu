@@ -89,8 +89,10 @@ cudaError_t kid_launch_build(uint64_t *slots, int log2_buckets, uint32_t *owner,
     const unsigned grid = 148 * 16;
     kid_build_claim_kernel<<<grid, 256, 0, stream>>>(slots, rem_bits, n_buckets - 1, owner, keys,
                                                       taxa, n_keys, (uint32_t)n_taxa, status);
+    KID_COUNT_LAUNCH();
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     kid_build_resolve_kernel<<<grid, 256, 0, stream>>>(slots, 4 * n_buckets, owner, taxa);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }

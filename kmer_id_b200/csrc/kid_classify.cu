@@ -266,6 +266,7 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
     if (blocks > need) blocks = need;
     if (blocks == 0) return cudaSuccess;
     kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 

@@ -22,6 +22,10 @@ struct KidClassifyParams {
     bool accept_u;
 };
 
+// every kernel launch of this library bumps this (bench.py reports it as gpu_launches)
+extern unsigned long long g_kid_kernel_launches;
+#define KID_COUNT_LAUNCH() (__atomic_add_fetch(&g_kid_kernel_launches, 1ULL, __ATOMIC_RELAXED))
+
 cudaError_t kid_launch_classify(const KidClassifyParams &p, int sm_count, cudaStream_t stream);
 
 // ---- table build (kid_build.cu) -----------------------------------------------------------------

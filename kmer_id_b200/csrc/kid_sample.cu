@@ -77,6 +77,7 @@ cudaError_t kid_launch_ucount(const uint64_t *slots, const uint32_t *seen, uint6
     if (n_words == 0) return cudaSuccess;
     kid_ucount_kernel<<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
         slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -86,6 +87,7 @@ cudaError_t kid_launch_seen_or(uint32_t *dst, const KidPtrList &src, int n_src, 
     if (n_words == 0) return cudaSuccess;
     kid_seen_or_kernel<<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
         reinterpret_cast<uint4 *>(dst), src, n_src, word0 / 4, n_words / 4);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -94,6 +96,7 @@ cudaError_t kid_launch_lookup(const KidTableView &t, const uint64_t *keys, size_
 {
     if (n == 0) return cudaSuccess;
     kid_lookup_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, keys, n, out);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -102,5 +105,6 @@ cudaError_t kid_launch_msca(const KidTreeView &t, const int32_t *x, const int32_
 {
     if (n == 0) return cudaSuccess;
     kid_msca_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, x, y, n, out);
+    KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
