@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-baseline-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="M", choices=["M", "K"], help="table layout (M = minimizer, default)")
+    ap.add_argument("--log2-sectors", type=int, default=0, help="table size override (0 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=80.0,
                     help="CPU seconds the reference arm may spend classifying (all steps together)")
     return ap.parse_args()
@@ -162,7 +164,8 @@ def run_ours(args):
     wl.db_device(local, dk, dt, stream=stream)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    db = kid.Database(dk, dt, parent, device=local, stream=stream)
+    db = kid.Database(dk, dt, parent, device=local, stream=stream, log2_sectors=args.log2_sectors,
+                      flags=kid.KID_DB_LAYOUT_KEYHASH if args.layout == "K" else 0)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     st = db.stats()
@@ -271,7 +274,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = lookups * SECTOR_BYTES / (kernel_ms / 1e3) / 1e9
     tr = traffic_per_lookup()
-    roofline = {"bound": "hbm", "kernel": "kid_classify_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "kid_classify2_kernel" if args.layout == "M" else "kid_classify_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tr["dram_bytes_per_lookup"] * lookups if tr else None),
                 "algorithmic_bytes_per_lookup": SECTOR_BYTES, "lookups_per_launch": lookups,
@@ -285,7 +288,7 @@ def run_ours(args):
         "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e,
         "gpu_launches": int(gpu_launches), "roofline": roofline,
         "lookups_per_s_whole_step": world * lookups / (ms_per_step / 1e3),
-        "table": {"bytes": st["table_bytes"], "distinct_keys": st["n_distinct"], "displaced": st["n_displaced"],
+        "table": {"layout": args.layout, "bytes": st["table_bytes"], "distinct_keys": st["n_distinct"], "displaced": st["n_displaced"],
                   "build_s": build_s},
         "hit_fraction": counters["hits"] / max(1, lookups),
         "classified_fraction": float((gcount[2:].sum()) / max(1, gcount.sum())),

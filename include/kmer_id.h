@@ -37,6 +37,10 @@ extern "C" {
 
 /* flags for kid_db_build */
 #define KID_DB_ACCEPT_U 1u /* reads: U/u count as T (kmer_read_vf6.cpp:496-500,521-525) */
+/* Table layout.  Default = "M": sectors addressed by the k-mer's minimizer so that neighbouring
+ * k-mers of a read share DRAM lines.  KID_DB_LAYOUT_KEYHASH = "K": one key-hashed 32-byte sector per
+ * lookup (the straightforward design, kept for the ncu bake-off in profiles/). Results are identical. */
+#define KID_DB_LAYOUT_KEYHASH 2u
 
 typedef struct kid_db kid_db;         /* GPU-resident probe table + taxonomy tree */
 typedef struct kid_sample kid_sample; /* per-sample accumulators: gcount, seen flags, counters */
@@ -60,25 +64,26 @@ void kid_host_free(void *p);
  *                     taxa[i] == 0 are invisible.  taxa[i] >= n_taxa -> KID_ERANGE.
  *   parent[t]         t = 0..n_taxa-1: Tree1::parent after all add_edge calls (default 1, :103).
  *   keys_on_device    non-zero if keys/taxa are device pointers (then they are read in place).
- *   log2_buckets      0 = choose from n_keys (load <= ~1/4 of 4-slot buckets); else 22..32.
+ *   log2_sectors      0 = size the table from n_keys; else log2 of the number of 32-byte sectors
+ *                     (layout M: 12..32, layout K: 22..32).
  */
 int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
-                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_buckets,
+                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_sectors,
                  void *stream, kid_db **out);
 void kid_db_free(kid_db *db);
 int kid_db_n_taxa(const kid_db *db);
 int kid_db_device(const kid_db *db);
-/* distinct visible keys, table buckets (32-byte sectors), table bytes, keys living outside their
- * home bucket */
-int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets,
+/* distinct visible keys, table sectors (32 bytes each), table bytes, keys living outside their
+ * home sector */
+int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_sectors,
                  uint64_t *table_bytes, uint64_t *n_displaced);
 /* Hashtable::getHash (:204-233) for n host keys -> host taxa (0 = absent). Test/diagnostic hook. */
 int kid_db_lookup(const kid_db *db, const uint64_t *keys, size_t n, uint32_t *taxa_out);
 /* Tree1::msca (:118-144) for n host pairs (x[i], y[i]) evaluated by the device routine. */
 int kid_db_msca(const kid_db *db, const int32_t *x, const int32_t *y, size_t n, int32_t *out);
-/* device address and size in 32-bit words of the table (for microbenchmarks such as the random
- * sector-gather ceiling in bench.py) */
-int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_buckets);
+/* device address and number of 32-byte sectors of the table (for microbenchmarks such as the
+ * random sector-gather ceiling in bench.py) */
+int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_sectors);
 
 /* ---- per-sample state ----------------------------------------------------------------------
  * replaces the globals gcount[], ucount[], kmer_seen (newkmer_10nx.cpp:61-64) and their reset in

@@ -67,6 +67,7 @@ for _name, (_res, _args) in _SIGS.items():
     _f.argtypes = _args
 
 KID_DB_ACCEPT_U = 1
+KID_DB_LAYOUT_KEYHASH = 2
 ERROR_NAMES = {-1: "KID_EINVAL", -2: "KID_ECUDA", -3: "KID_ENOMEM", -4: "KID_ERANGE",
                -5: "KID_ETREE", -6: "KID_EFULL"}
 
@@ -112,7 +113,7 @@ class Database:
     """GPU-resident probe table + taxonomy (Hashtable + Tree1 of the reference)."""
 
     def __init__(self, keys, taxa, parent: np.ndarray, device: int = 0, flags: int = 0,
-                 log2_buckets: int = 0, stream: int = 0):
+                 log2_sectors: int = 0, stream: int = 0):
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         on_device = not isinstance(keys, np.ndarray)
         if on_device:
@@ -126,7 +127,7 @@ class Database:
         self._h = _vp()
         _check(lib.kid_db_build(_as_ptr(keys) if n else None, _as_ptr(taxa) if n else None, n,
                                 int(on_device), _np_ptr(parent), parent.size, device, flags,
-                                log2_buckets, stream or None, C.byref(self._h)))
+                                log2_sectors, stream or None, C.byref(self._h)))
         self.n_taxa = parent.size
         self.device = device
 
@@ -140,7 +141,7 @@ class Database:
     def stats(self) -> dict:
         a, b, c, d = _u64(), _u64(), _u64(), _u64()
         _check(lib.kid_db_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return {"n_distinct": a.value, "n_buckets": b.value, "table_bytes": c.value,
+        return {"n_distinct": a.value, "n_sectors": b.value, "table_bytes": c.value,
                 "n_displaced": d.value}
 
     def table_device(self) -> Tuple[int, int]:

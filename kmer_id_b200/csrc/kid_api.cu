@@ -61,15 +61,21 @@ struct HostSlot { // one half of kid_classify_host's double buffer
 struct kid_db {
     int device = 0;
     int n_taxa = 0;
-    int log2_buckets = 0;
+    int layout = KID_LAYOUT_MINIMIZER;
+    int log2_sectors = 0;
     int sm_count = 148;
+    int max_probe = 0;
     unsigned flags = 0;
-    uint64_t n_buckets = 0;
-    uint64_t *slots = nullptr;
+    uint64_t n_sectors = 0;     // 32-byte sectors (layout K: 4 slots each, layout M: 2 entries each)
+    uint64_t *slots = nullptr;  // layout K
+    uint4 *entries = nullptr;   // layout M
     uint2 *tree = nullptr;
     uint64_t n_distinct = 0, n_displaced = 0;
 
-    KidTableView table_view() const { return KidTableView{ slots, n_buckets - 1, 60 - log2_buckets }; }
+    uint64_t n_slots() const { return layout == KID_LAYOUT_KEYHASH ? 4 * n_sectors : 2 * n_sectors; }
+    const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
+    KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
+    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - 2), max_probe }; }
     KidTreeView tree_view() const { return KidTreeView{ tree, n_taxa }; }
 };
 
@@ -155,7 +161,7 @@ static int build_tree_host(const int32_t *parent, int n_taxa, std::vector<uint2>
 }
 
 int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
-                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_buckets,
+                 const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_sectors,
                  void *stream_, kid_db **out)
 {
     if (!out) return fail(KID_EINVAL, "kid_db_build: out is NULL");
@@ -165,9 +171,11 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     if (!parent) return fail(KID_EINVAL, "kid_db_build: parent is NULL");
     if (n_keys && (!keys || !taxa)) return fail(KID_EINVAL, "kid_db_build: keys/taxa NULL");
     if (n_keys >= 0xFFFFFFFFull) return fail(KID_EINVAL, "kid_db_build: more than 2^32-2 probe entries");
-    if (log2_buckets && (log2_buckets < KID_MIN_LOG2_BUCKETS || log2_buckets > KID_MAX_LOG2_BUCKETS))
-        return fail(KID_EINVAL, "kid_db_build: log2_buckets %d outside [%d,%d]", log2_buckets,
-                    KID_MIN_LOG2_BUCKETS, KID_MAX_LOG2_BUCKETS);
+    const int layout = (flags & KID_DB_LAYOUT_KEYHASH) ? KID_LAYOUT_KEYHASH : KID_LAYOUT_MINIMIZER;
+    const int lo = layout == KID_LAYOUT_KEYHASH ? KID_MIN_LOG2_BUCKETS : KID2_MIN_LOG2_LINES + 2;
+    const int hi = layout == KID_LAYOUT_KEYHASH ? KID_MAX_LOG2_BUCKETS : KID2_MAX_LOG2_LINES + 2;
+    if (log2_sectors && (log2_sectors < lo || log2_sectors > hi))
+        return fail(KID_EINVAL, "kid_db_build: log2_sectors %d outside [%d,%d] for this layout", log2_sectors, lo, hi);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(KID_ECUDA, "kid_db_build: no CUDA device (this library has no CPU path)");
@@ -181,11 +189,13 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     if (!guard.ok) return fail(KID_ECUDA, "cudaSetDevice(%d) failed", device);
     cudaStream_t stream = (cudaStream_t)stream_;
 
-    const bool fixed = log2_buckets != 0;
-    int B = log2_buckets;
-    if (!fixed) { // about one key per 4-slot bucket: a second sector is needed by ~1 % of lookups
-        B = KID_MIN_LOG2_BUCKETS;
-        while (B < KID_MAX_LOG2_BUCKETS && ((uint64_t)1 << B) < n_keys) B++;
+    const bool fixed = log2_sectors != 0;
+    int B = log2_sectors;
+    if (!fixed) {
+        // layout K: ~1 key per 4-slot sector.  layout M: ~0.8 keys per 2-slot sector (3.3 per line)
+        B = lo;
+        const double per_sector = layout == KID_LAYOUT_KEYHASH ? 1.0 : 0.825;
+        while (B < hi && (double)((uint64_t)1 << B) * per_sector < (double)n_keys) B++;
     }
 
     kid_db *db = new (std::nothrow) kid_db;
@@ -193,13 +203,14 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     db->device = device;
     db->n_taxa = n_taxa;
     db->flags = flags;
+    db->layout = layout;
     cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device);
 
     const uint64_t *dkeys = keys;
     const uint32_t *dtaxa = taxa;
     uint64_t *tmp_keys = nullptr;
     uint32_t *tmp_taxa = nullptr, *owner = nullptr;
-    KidBuildStatus *dstatus = nullptr;
+    void *dstatus = nullptr;
     auto cleanup_tmp = [&]() {
         cudaFree(tmp_keys); cudaFree(tmp_taxa); cudaFree(owner); cudaFree(dstatus);
         tmp_keys = nullptr; tmp_taxa = nullptr; owner = nullptr; dstatus = nullptr;
@@ -224,36 +235,59 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         dkeys = tmp_keys;
         dtaxa = tmp_taxa;
     }
-    KID_CUDA_B(cudaMalloc(&dstatus, sizeof(KidBuildStatus)));
+    KID_CUDA_B(cudaMalloc(&dstatus, 64));
 
     for (;;) {
-        const uint64_t n_buckets = (uint64_t)1 << B;
-        const size_t n_slots = (size_t)(4 * n_buckets);
-        KID_CUDA_B(cudaMalloc(&db->slots, n_slots * sizeof(uint64_t)));
-        KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
-        KID_CUDA_B(cudaMemsetAsync(db->slots, 0, n_slots * sizeof(uint64_t), stream));
-        KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
-        KID_CUDA_B(cudaMemsetAsync(dstatus, 0, sizeof(KidBuildStatus), stream));
-        KID_CUDA_B(kid_launch_build(db->slots, B, owner, dkeys, dtaxa, n_keys, n_taxa, dstatus, stream));
-        KidBuildStatus st;
-        KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
-        KID_CUDA_B(cudaStreamSynchronize(stream));
-        cudaFree(owner);
-        owner = nullptr;
-        if (st.range_error)
-            return bail(fail(KID_ERANGE, "probe table: a probe names a taxon >= n_taxa (%d); the "
-                                         "reference indexes gcount[] out of bounds here", n_taxa));
-        if (!st.overflow) {
-            db->log2_buckets = B;
-            db->n_buckets = n_buckets;
+        const uint64_t n_sectors = (uint64_t)1 << B;
+        bool range_error = false, overflow = false;
+        KID_CUDA_B(cudaMemsetAsync(dstatus, 0, 64, stream));
+        if (layout == KID_LAYOUT_KEYHASH) {
+            const size_t n_slots = (size_t)(4 * n_sectors);
+            KID_CUDA_B(cudaMalloc(&db->slots, n_slots * sizeof(uint64_t)));
+            KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
+            KID_CUDA_B(cudaMemsetAsync(db->slots, 0, n_slots * sizeof(uint64_t), stream));
+            KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
+            KID_CUDA_B(kid_launch_build(db->slots, B, owner, dkeys, dtaxa, n_keys, n_taxa,
+                                        static_cast<KidBuildStatus *>(dstatus), stream));
+            KidBuildStatus st;
+            KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
+            KID_CUDA_B(cudaStreamSynchronize(stream));
+            cudaFree(owner);
+            owner = nullptr;
+            range_error = st.range_error;
+            overflow = st.overflow;
             db->n_distinct = st.n_distinct;
             db->n_displaced = st.n_displaced;
+            db->max_probe = KID_MAX_DISP;
+        } else {
+            const size_t n_entries = (size_t)(2 * n_sectors);
+            KID_CUDA_B(cudaMalloc(&db->entries, n_entries * sizeof(uint4)));
+            KID_CUDA_B(kid_launch_fill2(db->entries, n_entries, stream));
+            KID_CUDA_B(kid_launch_build2(db->entries, B - 2, dkeys, dtaxa, n_keys, n_taxa,
+                                         static_cast<Kid2BuildStatus *>(dstatus), stream));
+            Kid2BuildStatus st;
+            KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
+            KID_CUDA_B(cudaStreamSynchronize(stream));
+            range_error = st.range_error;
+            overflow = st.overflow;
+            db->n_distinct = st.n_distinct;
+            db->n_displaced = st.n_displaced;
+            db->max_probe = (int)st.max_probe;
+        }
+        if (range_error)
+            return bail(fail(KID_ERANGE, "probe table: a probe names a taxon >= n_taxa (%d); the "
+                                         "reference indexes gcount[] out of bounds here", n_taxa));
+        if (!overflow) {
+            db->log2_sectors = B;
+            db->n_sectors = n_sectors;
             break;
         }
         cudaFree(db->slots);
+        cudaFree(db->entries);
         db->slots = nullptr;
-        if (fixed || B == KID_MAX_LOG2_BUCKETS)
-            return bail(fail(KID_EFULL, "probe table: 2^%d buckets cannot place every key", B));
+        db->entries = nullptr;
+        if (fixed || B == hi)
+            return bail(fail(KID_EFULL, "probe table: 2^%d sectors cannot place every key", B));
         B++;
     }
     cleanup_tmp();
@@ -267,6 +301,7 @@ void kid_db_free(kid_db *db)
     if (!db) return;
     DeviceGuard guard(db->device);
     cudaFree(db->slots);
+    cudaFree(db->entries);
     cudaFree(db->tree);
     delete db;
 }
@@ -279,8 +314,8 @@ int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets, ui
 {
     if (!db) return fail(KID_EINVAL, "kid_db_stats: db is NULL");
     if (n_distinct) *n_distinct = db->n_distinct;
-    if (n_buckets) *n_buckets = db->n_buckets;
-    if (table_bytes) *table_bytes = db->n_buckets * 32;
+    if (n_buckets) *n_buckets = db->n_sectors;
+    if (table_bytes) *table_bytes = db->n_sectors * 32;
     if (n_displaced) *n_displaced = db->n_displaced;
     return KID_OK;
 }
@@ -288,8 +323,8 @@ int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets, ui
 int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_buckets)
 {
     if (!db || !table) return fail(KID_EINVAL, "kid_db_table_device: NULL argument");
-    *table = db->slots;
-    if (n_buckets) *n_buckets = db->n_buckets;
+    *table = const_cast<void *>(db->table_ptr());
+    if (n_buckets) *n_buckets = db->n_sectors;
     return KID_OK;
 }
 
@@ -303,7 +338,9 @@ int kid_db_lookup(const kid_db *db, const uint64_t *keys, size_t n, uint32_t *ta
     KID_CUDA(cudaMalloc(&dk, n * sizeof(uint64_t)));
     cudaError_t e = cudaMalloc(&dt, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpy(dk, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = kid_launch_lookup(db->table_view(), dk, n, dt, nullptr);
+    if (e == cudaSuccess)
+        e = db->layout == KID_LAYOUT_KEYHASH ? kid_launch_lookup(db->table_view(), dk, n, dt, nullptr)
+                                             : kid_launch_lookup2(db->table_view2(), dk, n, dt, nullptr);
     if (e == cudaSuccess) e = cudaMemcpy(taxa_out, dt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     cudaFree(dk);
     cudaFree(dt);
@@ -339,7 +376,7 @@ int kid_sample_create(const kid_db *db, kid_sample **out)
     kid_sample *s = new (std::nothrow) kid_sample;
     if (!s) return fail(KID_ENOMEM, "kid_sample_create: host allocation failed");
     s->db = db;
-    const uint64_t n_slots = 4 * db->n_buckets;
+    const uint64_t n_slots = db->n_slots();
     s->n_words = ((n_slots / 32) + 1023) / 1024 * 1024;
     cudaError_t e = cudaMalloc(&s->gcount, sizeof(int) * (size_t)db->n_taxa);
     if (e == cudaSuccess) e = cudaMalloc(&s->ucount, sizeof(int) * (size_t)db->n_taxa);
@@ -384,12 +421,19 @@ int kid_sample_begin(kid_sample *s, void *stream_)
     return KID_OK;
 }
 
+static cudaError_t launch_classify(const kid_db *db, const KidClassifyParams &p, cudaStream_t stream)
+{
+    return db->layout == KID_LAYOUT_KEYHASH ? kid_launch_classify(p, db->sm_count, stream)
+                                            : kid_launch_classify2(p, db->sm_count, stream);
+}
+
 static KidClassifyParams make_params(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
                                      const uint64_t *off, uint64_t bias, size_t n, int32_t *out_taxon,
                                      uint32_t *out_span)
 {
     KidClassifyParams p;
     p.table = s->db->table_view();
+    p.table2 = s->db->table_view2();
     p.tree = s->db->tree_view();
     p.seq = seq;
     p.qual = qual;
@@ -413,7 +457,7 @@ int kid_classify_device(kid_sample *s, const uint8_t *seq, const uint8_t *qual, 
     if (!seq || !off) return fail(KID_EINVAL, "kid_classify_device: seq/off is NULL");
     DeviceGuard guard(s->db->device);
     KidClassifyParams p = make_params(s, seq, qual, off, 0, n_reads, out_taxon, out_span);
-    KID_CUDA(kid_launch_classify(p, s->db->sm_count, (cudaStream_t)stream));
+    KID_CUDA(launch_classify(s->db, p, (cudaStream_t)stream));
     return KID_OK;
 }
 
@@ -484,7 +528,7 @@ int kid_classify_host(kid_sample *s, const uint8_t *seq, const uint8_t *qual, co
         KidClassifyParams p = make_params(s, h.seq, qual ? h.qual : nullptr, h.off, b0, n,
                                           out_taxon ? h.out_taxon : nullptr,
                                           out_span ? h.out_span : nullptr);
-        KID_CUDA(kid_launch_classify(p, s->db->sm_count, h.stream));
+        KID_CUDA(launch_classify(s->db, p, h.stream));
         if (out_taxon) {
             KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
             s->d2h += sizeof(int32_t) * n;
@@ -508,7 +552,8 @@ int kid_sample_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *str
     const size_t nb = sizeof(int) * (size_t)s->db->n_taxa;
     if (ucount) {
         KID_CUDA(cudaMemsetAsync(s->ucount, 0, nb, stream));
-        KID_CUDA(kid_launch_ucount(s->db->slots, s->seen, 0, s->n_words, s->ucount, s->db->n_taxa, stream));
+        KID_CUDA(kid_launch_ucount(s->db->table_ptr(), s->db->layout, s->seen, 0, s->n_words, s->ucount,
+                                   s->db->n_taxa, stream));
         KID_CUDA(cudaMemcpyAsync(ucount, s->ucount, nb, cudaMemcpyDeviceToHost, stream));
     }
     if (gcount) KID_CUDA(cudaMemcpyAsync(gcount, s->gcount, nb, cudaMemcpyDeviceToHost, stream));
@@ -574,7 +619,8 @@ int kid_ucount_range_device(const kid_db *db, const uint32_t *seen, uint64_t wor
     if (!db || !seen || !ucount_partial) return fail(KID_EINVAL, "kid_ucount_range_device: NULL argument");
     if ((word0 | n_words) & 3) return fail(KID_EINVAL, "kid_ucount_range_device: range must be multiples of 4 words");
     DeviceGuard guard(db->device);
-    KID_CUDA(kid_launch_ucount(db->slots, seen, word0, n_words, ucount_partial, db->n_taxa, (cudaStream_t)stream));
+    KID_CUDA(kid_launch_ucount(db->table_ptr(), db->layout, seen, word0, n_words, ucount_partial, db->n_taxa,
+                               (cudaStream_t)stream));
     return KID_OK;
 }
 

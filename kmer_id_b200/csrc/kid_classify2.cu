@@ -1,0 +1,420 @@
+// kid_classify2.cu - the per-read hot path over the minimizer-addressed table (kid_table2.cuh).
+//
+// Replaces, for a whole batch of reads, process_qual (newkmer_10nx.cpp:714-760), process_read
+// (:452-617), Hashtable::getHash (:204-233) and Tree1::msca (:118-144).
+//
+// One warp owns one read at a time (persistent grid, warp-strided reads); lane j of chunk c owns
+// the k-mer that starts at base 32c+j.
+//   LOAD    as soon as the read's offsets are known the warp issues, together, the coalesced
+//           128-bit loads of its bases and two 32-byte loads of its first/last quality bytes.
+//   TRIM    the four `while` loops of process_qual (:727-753) are "first/last position with a
+//           property" searches; the common case is answered from the two preloaded quality
+//           registers with ballots and shuffles, the rest by a 32-positions-per-step scan.
+//   STAGE   each lane packs its 16 bases into 2-bit codes + an ACGT-validity mask in a per-warp
+//           shared-memory strip (512 bases per window).
+//   KEYS    three LDS + two funnel shifts give the 64 bits that start at the lane's base: the top
+//           32 are its 16-mer (minimizer candidate), the top 60 its forward k-mer (:481-517);
+//           __brevll gives the reverse complement, min() the canonical key (:528).
+//   MINIM   sliding minimum of the 16-mer hashes over 15 positions with 4 shuffle rounds
+//           (1,2,4,7) across 4 chunks + a 14-lane halo: M(key) without looking at the key.
+//   LOOKUP  sector = 4*line(M) + sector(key); four chunks (128 k-mers) request their 32-byte
+//           sectors before the first is consumed.  Lanes that share a minimizer share a line, so
+//           a warp-wide load touches ~5 lines instead of 32.
+//   FOLD    hits are rare; a ballot finds them and the warp folds them strictly in position order
+//           with kid_msca (the fold is order dependent).
+//   COUNT   seen bit (atomicOr on the per-sample bitmap) for hits with taxon > 1 (:596-603),
+//           gcount[final]++ (:613) in a shared-memory histogram flushed once per block.
+#include "kid_kernels.cuh"
+
+#include <type_traits>
+
+namespace {
+
+constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
+constexpr int kWindowStarts = 448; // k-mer starts per staged window: 15 + 447 + 14 + 15 < 512
+constexpr int kCodeWords = 40; // 32 + zero padding so that halo lanes never need a bounds check
+constexpr int kValidWords = 20; // 16 + zero padding
+constexpr int kUnroll = 4;
+
+struct WarpStrip {
+    uint32_t codes[kCodeWords];
+    uint32_t valid[kValidWords];
+    uint32_t kmask[kValidWords];
+};
+
+__device__ __forceinline__ void pack4(uint32_t x, bool accept_u, uint32_t &code8, uint32_t &valid4)
+{
+    const uint32_t up = x & 0xDFDFDFDFu;
+    uint32_t ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) |
+                  __vcmpeq4(up, 0x47474747u) | __vcmpeq4(up, 0x54545454u);
+    if (accept_u) ok |= __vcmpeq4(up, 0x55555555u);
+    uint32_t c = (x >> 1) & 0x03030303u; // A0 C1 T/U2 G3, then swap 2<->3 -> A0 C1 G2 T3 (:480-519)
+    c ^= (c >> 1) & 0x01010101u;
+    code8 = (c * 0x40100401u) >> 24;
+    valid4 = ((ok & 0x01010101u) * 0x08040201u) >> 24 & 0xFu;
+}
+
+// generic 32-positions-per-step scans (fallbacks of the trim fast path) -----------------------
+__device__ __forceinline__ int scan_first_good(const signed char *q, int from, int stop, int lane)
+{ // first i in [from, stop) with q[i] >= '1', else stop
+    for (int base = from; base < stop; base += 32) {
+        const int i = base + lane;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, i < stop && q[i] >= 49);
+        if (m) return base + __ffs(m) - 1;
+    }
+    return stop;
+}
+__device__ __forceinline__ int scan_last_good(const signed char *q, int from, int start, int lane)
+{ // last i in (start, from] with q[i] >= '1', else start
+    for (int hi = from; hi > start; hi -= 32) {
+        const int i = hi - lane;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, i > start && q[i] >= 49);
+        if (m) return hi - (__ffs(m) - 1);
+    }
+    return start;
+}
+__device__ __forceinline__ int scan_window_fwd(const signed char *q, int start, int lim, int lane)
+{ // first s in [start, lim) whose 4-window sum(q-32) >= 68, else lim
+    for (int base = start; base < lim; base += 32) {
+        const int s = base + lane;
+        bool ok = false;
+        if (s < lim) ok = (int)q[s] + q[s + 1] + q[s + 2] + q[s + 3] - 128 >= 68;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) return base + __ffs(m) - 1;
+    }
+    return lim;
+}
+__device__ __forceinline__ int scan_window_bwd(const signed char *q, int stop, int lo, int lane)
+{ // last t in (lo, stop] whose trailing 4-window sum >= 68, else lo
+    for (int hi = stop; hi > lo; hi -= 32) {
+        const int t = hi - lane;
+        bool ok = false;
+        if (t > lo) ok = (int)q[t] + q[t - 1] + q[t - 2] + q[t - 3] - 128 >= 68;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) return hi - (__ffs(m) - 1);
+    }
+    return lo;
+}
+
+template <bool HAS_QUAL, bool SMEM_HIST>
+__global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 3)
+kid_classify2_kernel(const KidClassifyParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpStrip *strips = reinterpret_cast<WarpStrip *>(smem_raw);
+    int *hist = reinterpret_cast<int *>(smem_raw + sizeof(WarpStrip) * kWarpsPerBlock);
+
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    WarpStrip &strip = strips[warp_in_block];
+    const unsigned full = 0xFFFFFFFFu;
+    const Kid2TableView tab = p.table2;
+
+    if (SMEM_HIST) {
+        for (int i = threadIdx.x; i < p.tree.n_taxa; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    if (lane < kCodeWords - 32) strip.codes[32 + lane] = 0;
+    if (lane < kValidWords - 16) { strip.valid[16 + lane] = 0; strip.kmask[16 + lane] = 0; }
+
+    unsigned lane_lookups = 0;        // per lane, reduced once at the end
+    unsigned long long n_hits = 0;    // warp-uniform
+
+    const size_t warps_total = (size_t)gridDim.x * kWarpsPerBlock;
+    for (size_t r = (size_t)blockIdx.x * kWarpsPerBlock + warp_in_block; r < p.n_reads;
+         r += warps_total) {
+        const uint64_t g0 = __ldg(p.off + r) - p.off_bias;
+        const int len = (int)(__ldg(p.off + r + 1) - p.off_bias - g0);
+        int start = 0, stop = len - 1;
+
+        // ---- LOAD: bases of window 0 and both quality ends, all independent of each other
+        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(p.seq) + g0;
+        const uintptr_t abase = addr0 & ~(uintptr_t)15;
+        const int delta = (int)(addr0 - abase); // staged index of base 0
+        const int staged_len = delta + len;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (16 * lane < staged_len) v = __ldg(reinterpret_cast<const uint4 *>(abase) + lane);
+
+        // ---- TRIM (:724-753)
+        if (HAS_QUAL && len > 0) {
+            const signed char *q = reinterpret_cast<const signed char *>(p.qual) + g0;
+            const int qa = lane < len ? (int)q[lane] : -128;           // q[0..31]
+            const int qb = lane < len ? (int)q[len - 1 - lane] : -128; // q[len-1 .. len-32]
+            { // while (qual[start] < '1' && start < stop) start++;
+                const unsigned m = __ballot_sync(full, lane < stop && qa >= 49);
+                start = m ? __ffs(m) - 1 : scan_first_good(q, 32, stop, lane);
+            }
+            { // while (qual[stop] < '1' && stop > start) stop--;
+                const unsigned m = __ballot_sync(full, len - 1 - lane > start && qb >= 49);
+                stop = m ? len - 1 - (__ffs(m) - 1) : scan_last_good(q, len - 33, start, lane);
+            }
+            if (start < stop - 4) { // leading 4-base window slides right while sum(q-32) < 68
+                const int lim = stop - 4, s = start + lane;
+                const int w = __shfl_sync(full, qa, s & 31) + __shfl_sync(full, qa, (s + 1) & 31) +
+                              __shfl_sync(full, qa, (s + 2) & 31) + __shfl_sync(full, qa, (s + 3) & 31);
+                const bool known = s + 3 < 32;
+                const unsigned mk = __ballot_sync(full, known && s < lim && w - 128 >= 68);
+                const unsigned unk = __ballot_sync(full, !known && s < lim);
+                if (mk && (!unk || __ffs(mk) < __ffs(unk))) start += __ffs(mk) - 1;
+                else if (!mk && !unk) start = lim;
+                else start = scan_window_fwd(q, start, lim, lane);
+            }
+            if (start < stop - 4) { // trailing window slides left
+                const int lo = start + 4, t = stop - lane;
+                const int idx = len - 1 - t; // lane of qb that holds q[t]
+                const int w = __shfl_sync(full, qb, idx & 31) + __shfl_sync(full, qb, (idx + 1) & 31) +
+                              __shfl_sync(full, qb, (idx + 2) & 31) + __shfl_sync(full, qb, (idx + 3) & 31);
+                const bool known = idx + 3 < 32;
+                const unsigned mk = __ballot_sync(full, known && t > lo && w - 128 >= 68);
+                const unsigned unk = __ballot_sync(full, !known && t > lo);
+                if (mk && (!unk || __ffs(mk) < __ffs(unk))) stop -= __ffs(mk) - 1;
+                else if (!mk && !unk) stop = lo;
+                else stop = scan_window_bwd(q, stop, lo, lane);
+            }
+        }
+        if (p.out_span && lane == 0) {
+            p.out_span[2 * r] = (uint32_t)start;
+            p.out_span[2 * r + 1] = (uint32_t)stop;
+        }
+        if (stop - start < KID_KSIZE) { // :755 - the read vanishes (also covers len <= 30)
+            if (p.out_taxon && lane == 0) p.out_taxon[r] = -1;
+            continue;
+        }
+
+        const int last_start = stop - (KID_KSIZE - 1); // last k-mer start position
+        uint32_t fin = 0;
+
+        for (int wb = 0; wb <= last_start; wb += kWindowStarts) {
+            if (wb + kWindowStarts <= start) continue; // window entirely before the trimmed span
+            __syncwarp();
+            if (wb > 0) {
+                v = make_uint4(0, 0, 0, 0);
+                if (wb + 16 * lane < staged_len)
+                    v = __ldg(reinterpret_cast<const uint4 *>(abase + (uintptr_t)wb) + lane);
+            }
+            { // STAGE
+                uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
+                pack4(v.x, p.accept_u, c0, v0);
+                pack4(v.y, p.accept_u, c1, v1);
+                pack4(v.z, p.accept_u, c2, v2);
+                pack4(v.w, p.accept_u, c3, v3);
+                strip.codes[lane] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+                const uint32_t v16 = (v0 << 12) | (v1 << 8) | (v2 << 4) | v3;
+                const uint32_t nb = __shfl_down_sync(full, v16, 1);
+                if ((lane & 1) == 0) strip.valid[lane >> 1] = (v16 << 16) | nb;
+            }
+            __syncwarp();
+
+            // k-mer starts of this window, relative to wb: [first, wcount)
+            const int wcount = min(kWindowStarts, last_start - wb + 1);
+            const int first = max(0, start - wb);
+            { // KMASK: bit (31 - t%32) of word t/32 <=> a valid, in-range k-mer starts at staged index t
+                const int l16 = lane & 15;
+                uint64_t x = ((uint64_t)strip.valid[l16] << 32) | strip.valid[l16 + 1];
+                x &= x << 1; x &= x << 2; x &= x << 4; x &= x << 8; // runs of 16 valid bases
+                x &= x << 14;                                       // runs of 30
+                uint32_t km = (uint32_t)(x >> 32);
+                const int lo_b = delta + first - 32 * l16;          // first allowed bit of this word
+                const int hi_b = delta + wcount - 1 - 32 * l16;     // last allowed bit
+                uint32_t allow = lo_b <= 0 ? 0xFFFFFFFFu : (lo_b >= 32 ? 0u : 0xFFFFFFFFu >> lo_b);
+                if (hi_b < 31) allow &= hi_b < 0 ? 0u : ~(0xFFFFFFFFu >> (hi_b + 1));
+                km &= allow;
+                if (lane < 16) {
+                    strip.kmask[lane] = km;
+                    lane_lookups += __popc(km); // every set bit is exactly one getHash call (:529)
+                }
+            }
+            __syncwarp();
+
+            auto block128 = [&](int c, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                // chunks (of 32 k-mers) this iteration has; FULL == all four, known at compile time
+                const int nch = FULL ? kUnroll : min(kUnroll, (wcount - c + 31) >> 5);
+                uint32_t cm[kUnroll + 1]; // 16-mer hashes -> sliding minima
+                uint64_t key[kUnroll];
+                // KEYS
+#pragma unroll
+                for (int u = 0; u <= kUnroll; u++) {
+                    cm[u] = 0xFFFFFFFFu;
+                    if (FULL || u <= nch) { // chunk nch is the 14-lane halo of chunk nch-1
+                        const int t = delta + c + 32 * u + lane; // staged index of this lane's base
+                        const int w = t >> 4, sh = (t & 15) * 2;
+                        const uint32_t w0 = strip.codes[w], w1 = strip.codes[w + 1];
+                        const uint32_t hi = __funnelshift_l(w1, w0, sh);
+                        const uint32_t rc = kid_rc16(hi);
+                        cm[u] = kid_mm_hash_canon(min(hi, rc));
+                        if (u < kUnroll) {
+                            // forward key = first 30 of the 32 bases at this position; the reverse
+                            // complement of 32 bases is rc16(low half) : rc16(high half) and its low
+                            // 60 bits are the reverse complement of the first 30 bases
+                            const uint32_t lo = __funnelshift_l(strip.codes[w + 2], w1, sh);
+                            const uint64_t kf = (((uint64_t)hi << 32) | lo) >> 4;
+                            const uint64_t kr = (((uint64_t)kid_rc16(lo) << 32) | rc) & KID_MASK60;
+                            key[u] = kf < kr ? kf : kr; // :528
+                        }
+                    }
+                }
+                // MINIM: window minimum over 15 consecutive positions (1 + 2 + 4 + 7 doubling)
+#pragma unroll
+                for (int step = 0; step < 4; step++) {
+                    const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
+                    const int src = (lane + d) & 31;
+                    const bool wrap = lane + d >= 32;
+                    uint32_t s[kUnroll + 1];
+#pragma unroll
+                    for (int u = 0; u <= kUnroll; u++)
+                        if (FULL || u <= nch) s[u] = __shfl_sync(full, cm[u], src);
+#pragma unroll
+                    for (int u = 0; u < kUnroll; u++)
+                        if (FULL || u < nch) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
+                    if (FULL) cm[kUnroll] = min(cm[kUnroll], wrap ? 0xFFFFFFFFu : s[kUnroll]);
+                    else {
+#pragma unroll
+                        for (int u = 1; u < kUnroll; u++)
+                            if (u == nch) cm[u] = min(cm[u], wrap ? 0xFFFFFFFFu : s[u]);
+                    }
+                }
+                // LOOKUP: issue every sector load (predicated, no branches) before consuming any
+                uint4 ea[kUnroll], eb[kUnroll];
+                uint32_t sec[kUnroll]; // sector index (< 2^32: at most 2^30 lines)
+                uint32_t act[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    act[u] = 0;
+                    if (FULL || u < nch) {
+                        const int t = delta + c + 32 * u + lane;
+                        act[u] = (strip.kmask[t >> 5] << (t & 31)) >> 31;
+                        const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
+                        sec[u] = (line << 2) | kid_key_sector(key[u]);
+                        kid2_load_sector_if(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u], act[u]);
+                    }
+                }
+                // MATCH round 1, branch free
+                uint32_t taxon[kUnroll], slotj[kUnroll], again = 0;
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    taxon[u] = 0; slotj[u] = 0;
+                    if (FULL || u < nch) {
+                        const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                        const bool h0 = act[u] && ea[u].x == klo && ea[u].y == khi;
+                        const bool h1 = act[u] && eb[u].x == klo && eb[u].y == khi;
+                        taxon[u] = h0 ? ea[u].z : (h1 ? eb[u].z : 0u);
+                        slotj[u] = h1 ? 1u : 0u;
+                        // full sector (both entries carry bit 63) without a match: the key may live
+                        // in a later sector
+                        const bool more = act[u] && !h0 && !h1 && (int32_t)(ea[u].y & eb[u].y) < 0;
+                        again |= more ? (1u << u) : 0u;
+                    }
+                }
+                // MATCH round 2 for the few lanes that met a full sector: all loads first
+                if (__any_sync(full, again != 0)) {
+#pragma unroll
+                    for (int u = 0; u < kUnroll; u++) {
+                        if (FULL || u < nch) {
+                            const uint32_t s2 = (uint32_t)(((uint64_t)sec[u] + 1) & tab.sector_mask);
+                            kid2_load_sector_if(tab.sectors + 2 * (uint64_t)s2, ea[u], eb[u], (again >> u) & 1u);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; u++) {
+                        if ((FULL || u < nch) && ((again >> u) & 1u)) {
+                            const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                            const bool h0 = ea[u].x == klo && ea[u].y == khi;
+                            const bool h1 = eb[u].x == klo && eb[u].y == khi;
+                            if (h0 || h1) {
+                                taxon[u] = h0 ? ea[u].z : eb[u].z;
+                                slotj[u] = h1 ? 1u : 0u;
+                                sec[u] = (uint32_t)(((uint64_t)sec[u] + 1) & tab.sector_mask);
+                            } else if ((int32_t)(ea[u].y & eb[u].y) < 0) { // rare: third sector and on
+                                uint64_t slot = 0;
+                                taxon[u] = kid2_lookup_from(tab, sec[u], key[u], 2, slot);
+                                sec[u] = (uint32_t)(slot >> 1);
+                                slotj[u] = (uint32_t)slot & 1u;
+                            }
+                        }
+                    }
+                }
+                // SEEN + FOLD, strictly in position order
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    if (!FULL && u >= nch) break; // warp-uniform
+                    unsigned m = __ballot_sync(full, taxon[u] > 0);
+                    if (m) {
+                        if (taxon[u] > 1) { // :596-603 - fire and forget, the OR is idempotent
+                            const uint64_t slot = 2 * (uint64_t)sec[u] + slotj[u];
+                            atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                        }
+                        n_hits += __popc(m);
+                        do { // ordered left fold over the hits of this chunk (:588-595)
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t tj = __shfl_sync(full, taxon[u], src);
+                            if (fin > 0) { if (tj != fin) fin = kid_msca(p.tree, tj, fin); }
+                            else fin = tj;
+                        } while (m);
+                    }
+                }
+            };
+
+            for (int c = (first / 32) * 32; c < wcount; c += 32 * kUnroll) {
+                if (wcount - c > 32 * (kUnroll - 1)) block128(c, std::true_type{});
+                else block128(c, std::false_type{});
+            }
+        }
+
+        // ---- COUNT (:613)
+        if (lane == 0) {
+            if (p.out_taxon) p.out_taxon[r] = (int32_t)fin;
+            if (SMEM_HIST) atomicAdd(&hist[fin], 1);
+            else atomicAdd(&p.gcount[fin], 1);
+        }
+    }
+
+    unsigned long long n_lookups = lane_lookups;
+    for (int o = 16; o; o >>= 1) n_lookups += __shfl_xor_sync(full, n_lookups, o);
+    if (lane == 0) {
+        if (n_lookups) atomicAdd(p.counters + 0, n_lookups);
+        if (n_hits) atomicAdd(p.counters + 1, n_hits);
+    }
+    if (SMEM_HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.tree.n_taxa; i += blockDim.x) {
+            const int cnt = hist[i];
+            if (cnt) atomicAdd(&p.gcount[i], cnt);
+        }
+    }
+}
+
+template <bool Q, bool H>
+cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t stream)
+{
+    const size_t smem = sizeof(WarpStrip) * kWarpsPerBlock + (H ? (size_t)p.tree.n_taxa * 4 : 0);
+    auto kern = kid_classify2_kernel<Q, H>;
+    cudaError_t err = cudaSuccess;
+    if (smem > 48 * 1024) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KID_CLASSIFY_THREADS, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    size_t blocks = (size_t)sm_count * per_sm; // persistent: a whole number of resident waves
+    const size_t need = (p.n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > need) blocks = need;
+    if (blocks == 0) return cudaSuccess;
+    kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaStream_t stream)
+{
+    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
+    if (p.qual) return hist ? launch_one<true, true>(p, sm_count, stream)
+                            : launch_one<true, false>(p, sm_count, stream);
+    return hist ? launch_one<false, true>(p, sm_count, stream)
+                : launch_one<false, false>(p, sm_count, stream);
+}

@@ -1,13 +1,17 @@
 // kid_kernels.cuh - launch interfaces between kid_api.cu and the kernel files.
 #pragma once
 #include "kid_common.cuh"
+#include "kid_table2.cuh"
 
 #define KID_KSIZE 30
 #define KID_CLASSIFY_THREADS 256
 #define KID_SMEM_HIST_MAX_BYTES (96u * 1024u) /* gcount histogram lives in smem up to 24576 taxa */
 
+enum KidLayout { KID_LAYOUT_MINIMIZER = 0, KID_LAYOUT_KEYHASH = 1 };
+
 struct KidClassifyParams {
-    KidTableView table;
+    KidTableView table;   // layout K (kid_common.cuh)
+    Kid2TableView table2; // layout M (kid_table2.cuh)
     KidTreeView tree;
     const uint8_t *seq;
     const uint8_t *qual; // NULL: no trimming
@@ -26,7 +30,8 @@ struct KidClassifyParams {
 extern unsigned long long g_kid_kernel_launches;
 #define KID_COUNT_LAUNCH() (__atomic_add_fetch(&g_kid_kernel_launches, 1ULL, __ATOMIC_RELAXED))
 
-cudaError_t kid_launch_classify(const KidClassifyParams &p, int sm_count, cudaStream_t stream);
+cudaError_t kid_launch_classify(const KidClassifyParams &p, int sm_count, cudaStream_t stream);  // layout K
+cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaStream_t stream); // layout M
 
 // ---- table build (kid_build.cu) -----------------------------------------------------------------
 struct KidBuildStatus {
@@ -40,8 +45,25 @@ cudaError_t kid_launch_build(uint64_t *slots, int log2_buckets, uint32_t *owner,
                              const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int n_taxa,
                              KidBuildStatus *status, cudaStream_t stream);
 
+// layout M: entries must be filled with {0, 0, 0xFFFFFFFF} (aux = owner), status zeroed
+struct Kid2BuildStatus {
+    unsigned long long n_distinct;
+    unsigned long long n_displaced; // keys outside their home sector
+    unsigned int max_probe;
+    unsigned int range_error;
+    unsigned int overflow;          // a key needed more than KID2_BUILD_MAX_PROBE sectors
+    unsigned int pad;
+};
+#define KID2_BUILD_MAX_PROBE 4096
+cudaError_t kid_launch_fill2(uint4 *entries, size_t n_entries, cudaStream_t stream);
+cudaError_t kid_launch_build2(uint4 *entries, int log2_lines, const uint64_t *keys, const uint32_t *taxa,
+                              size_t n_keys, int n_taxa, Kid2BuildStatus *status, cudaStream_t stream);
+cudaError_t kid_launch_lookup2(const Kid2TableView &t, const uint64_t *keys, size_t n, uint32_t *out,
+                               cudaStream_t stream);
+
 // ---- sample-end kernels (kid_sample.cu) ------------------------------------------------------------
-cudaError_t kid_launch_ucount(const uint64_t *slots, const uint32_t *seen, uint64_t word0,
+// slots: layout K = uint64 entries, layout M = 16-byte entries (taxon in the third word)
+cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *seen, uint64_t word0,
                               uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream);
 #define KID_MAX_OR_SOURCES 16
 struct KidPtrList {

@@ -7,8 +7,9 @@
 
 namespace {
 
+template <int LAYOUT>
 __global__ void __launch_bounds__(256)
-kid_ucount_kernel(const uint64_t *__restrict__ slots, const uint4 *__restrict__ seen4,
+kid_ucount_kernel(const void *__restrict__ slots_, const uint4 *__restrict__ seen4,
                   uint64_t quad0, uint64_t n_quads, int *ucount, int n_taxa)
 {
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
@@ -23,7 +24,11 @@ kid_ucount_kernel(const uint64_t *__restrict__ slots, const uint4 *__restrict__ 
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const uint64_t slot = ((quad0 + q) * 4 + k) * 32 + b;
-                const uint32_t taxon = (uint32_t)__ldg(slots + slot) & KID_TAXON_MASK;
+                uint32_t taxon;
+                if (LAYOUT == KID_LAYOUT_KEYHASH)
+                    taxon = (uint32_t)__ldg(static_cast<const uint64_t *>(slots_) + slot) & KID_TAXON_MASK;
+                else
+                    taxon = __ldg(static_cast<const uint4 *>(slots_) + slot).z;
                 if (taxon < (uint32_t)n_taxa) atomicAdd(ucount + taxon, 1);
             }
         }
@@ -54,6 +59,16 @@ __global__ void kid_lookup_kernel(KidTableView t, const uint64_t *keys, size_t n
     }
 }
 
+__global__ void kid_lookup2_kernel(Kid2TableView t, const uint64_t *keys, size_t n, uint32_t *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i] & KID_MASK60;
+        uint64_t slot;
+        out[i] = kid2_lookup_from(t, kid2_home_sector(kid_minimizer(key), key, t.line_shift), key, 0, slot);
+    }
+}
+
 __global__ void kid_msca_kernel(KidTreeView t, const int32_t *x, const int32_t *y, size_t n,
                                 int32_t *out)
 {
@@ -71,12 +86,16 @@ unsigned grid_for(uint64_t n, unsigned threads)
 
 } // namespace
 
-cudaError_t kid_launch_ucount(const uint64_t *slots, const uint32_t *seen, uint64_t word0,
+cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *seen, uint64_t word0,
                               uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
-    kid_ucount_kernel<<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-        slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+    if (layout == KID_LAYOUT_KEYHASH)
+        kid_ucount_kernel<KID_LAYOUT_KEYHASH><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+    else
+        kid_ucount_kernel<KID_LAYOUT_MINIMIZER><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
     KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -96,6 +115,15 @@ cudaError_t kid_launch_lookup(const KidTableView &t, const uint64_t *keys, size_
 {
     if (n == 0) return cudaSuccess;
     kid_lookup_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, keys, n, out);
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_lookup2(const Kid2TableView &t, const uint64_t *keys, size_t n, uint32_t *out,
+                               cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    kid_lookup2_kernel<<<grid_for(n, 256), 256, 0, stream>>>(t, keys, n, out);
     KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }

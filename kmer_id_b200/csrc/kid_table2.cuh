@@ -1,0 +1,146 @@
+// kid_table2.cuh - the minimizer-addressed probe table ("layout M", the default).
+//
+// Why: ncu on the key-hashed table (kid_common.cuh, "layout K") shows every lookup pulling its own
+// 128-byte line from DRAM (profiles/r1_v1_keyhash_classify_ncu.txt: 4 DRAM sectors per lookup), and
+// the chip serves only ~37.8 G such independent requests per second whatever their size
+// (profiles/r1_gather_microbench_ncu.txt).  One request per lookup therefore caps the path at
+// ~38 G lookups/s.  The only way up is to make consecutive k-mers of a read share requests.
+//
+// How: the home of a key is chosen by its MINIMIZER, not by the key itself.
+//   c(i)     = kid_mm_hash(canonical 16-mer starting at base i)        i = 0..14 within the 30-mer
+//   M(key)   = min_i c(i)                                              strand independent
+//   line     = (M * 0x9E3779B1) >> (32 - L)                            2^L lines of 128 bytes
+//   sector   = 4 * line + kid_key_sector(key)                          4 sectors per line
+//   entry    = { key | 1<<63 , taxon , 0 }  16 bytes, 2 per 32-byte sector, 8 per line
+// Adjacent k-mers of a read share their minimizer in runs of ~7.5, so the 32 lanes of a warp (32
+// consecutive k-mers) touch ~5 distinct lines instead of 32: ~6.5x fewer DRAM line fetches and
+// L2 requests per lookup.  Within the line the key picks the sector, so one lane still reads just
+// 32 bytes, and a genome region whose k-mers share a minimizer spreads over the line's 8 slots.
+// A key that finds its sector full moves to the next sector (linear probing in sector units);
+// sectors only ever fill up, so a lookup stops at the first sector that has an empty slot.
+// Full 60-bit keys are stored, so a match is exact by construction (no fingerprints).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define KID_MM 16                       /* minimizer length in bases */
+#define KID_MM_WINDOWS (30 - KID_MM + 1) /* 15 candidate 16-mers per 30-mer */
+#define KID2_OCC (1ULL << 63)
+#define KID2_MIN_LOG2_LINES 10
+#define KID2_MAX_LOG2_LINES 30 /* sector indices stay below 2^32 */
+
+struct Kid2Entry {
+    uint64_t keyword; // key | KID2_OCC, 0 = empty
+    uint32_t taxon;
+    uint32_t aux;
+};
+
+struct Kid2TableView {
+    const uint4 *sectors; // 2 uint4 (= 2 entries) per sector
+    uint64_t sector_mask; // n_sectors - 1
+    int line_shift;       // 32 - log2_lines
+    int max_probe;        // longest displacement (in sectors) any key needed at build time
+};
+
+// reverse complement of a 16-mer held in 32 bits (first base in the top pair)
+__host__ __device__ __forceinline__ uint32_t kid_rc16(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t y = __brev(x);
+#else
+    uint32_t y = x;
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    y = ((y >> 2) & 0x33333333u) | ((y & 0x33333333u) << 2);
+    y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);
+    y = ((y >> 8) & 0x00FF00FFu) | ((y & 0x00FF00FFu) << 8);
+    y = (y >> 16) | (y << 16);
+#endif
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    return ~y;
+}
+
+// ordering hash of a canonical 16-mer (only its order matters; it need not be a bijection)
+__host__ __device__ __forceinline__ uint32_t kid_mm_hash_canon(uint32_t x)
+{
+    x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x85EBCA77u;
+    x ^= x >> 13;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t kid_mm_hash(uint32_t fwd16)
+{
+    const uint32_t rc = kid_rc16(fwd16);
+    return kid_mm_hash_canon(fwd16 < rc ? fwd16 : rc);
+}
+
+// minimizer hash of a 60-bit key (build side; the classify kernel slides it along the read)
+__host__ __device__ __forceinline__ uint32_t kid_minimizer(uint64_t key)
+{
+    uint32_t m = 0xFFFFFFFFu;
+    for (int i = 0; i < KID_MM_WINDOWS; i++) {
+        const uint32_t c = kid_mm_hash((uint32_t)(key >> (2 * (KID_MM_WINDOWS - 1 - i))));
+        m = c < m ? c : m;
+    }
+    return m;
+}
+
+__host__ __device__ __forceinline__ uint32_t kid_key_sector(uint64_t key)
+{
+    return (((uint32_t)key ^ (uint32_t)(key >> 32)) * 0xC2B2AE35u) >> 30;
+}
+
+__host__ __device__ __forceinline__ uint64_t kid2_home_sector(uint32_t minimizer, uint64_t key,
+                                                              int line_shift)
+{
+    const uint32_t line = line_shift >= 32 ? 0u : (minimizer * 0x9E3779B1u) >> line_shift;
+    return ((uint64_t)line << 2) | kid_key_sector(key);
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void kid2_load_sector(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
+// same, but only lanes with pred != 0 issue the load (a/b keep their values otherwise): no branch
+__device__ __forceinline__ void kid2_load_sector_if(const uint4 *p, uint4 &a, uint4 &b, uint32_t pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+                 "@q ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w)
+                 : "l"(p), "r"(pred));
+}
+
+// 1 = hit (taxon, slot_in_sector), 0 = final miss (an empty slot), -1 = full sector without match
+__device__ __forceinline__ int kid2_match(const uint4 &a, const uint4 &b, uint32_t want_lo,
+                                          uint32_t want_hi, uint32_t &taxon, int &j)
+{
+    if (a.x == want_lo && a.y == want_hi) { taxon = a.z; j = 0; return 1; }
+    if (b.x == want_lo && b.y == want_hi) { taxon = b.z; j = 1; return 1; }
+    // occupied entries carry bit 63: both high words negative <=> sector full
+    return ((int32_t)(a.y & b.y) < 0) ? -1 : 0;
+}
+
+// continue a lookup from sector `s` (used for the rare full sectors and by the diagnostic kernel)
+__device__ __forceinline__ uint32_t kid2_lookup_from(const Kid2TableView &t, uint64_t s, uint64_t key,
+                                                     int probes_done, uint64_t &slot)
+{
+    const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32) | 0x80000000u;
+    for (int d = probes_done; d <= t.max_probe; d++) {
+        const uint64_t sec = (s + (uint64_t)d) & t.sector_mask;
+        uint4 a, b;
+        kid2_load_sector(t.sectors + 2 * sec, a, b);
+        uint32_t taxon;
+        int j;
+        const int r = kid2_match(a, b, lo, hi, taxon, j);
+        if (r > 0) { slot = 2 * sec + (uint64_t)j; return taxon; }
+        if (r == 0) return 0;
+    }
+    return 0;
+}
+
+#endif // __CUDACC__

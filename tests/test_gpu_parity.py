@@ -9,6 +9,13 @@ import helpers as H
 
 pytestmark = pytest.mark.gpu
 
+LAYOUT_M, LAYOUT_K = 0, 2  # KID_DB_LAYOUT_KEYHASH = 2
+
+
+@pytest.fixture(params=[LAYOUT_M, LAYOUT_K], ids=["layoutM", "layoutK"])
+def layout(request):
+    return request.param
+
 
 def _oracle(db, flags=0):
     from oracle import kor
@@ -45,11 +52,11 @@ def _check_counts(gs, osamp):
     assert c["reads"] == osamp.tct
 
 
-def test_lookup_first_wins_and_zero_taxon():
+def test_lookup_first_wins_and_zero_taxon(layout):
     rng = np.random.default_rng(7)
     db = H.make_db(rng, 50000, n_dup=5000, n_zero=400)
     odb, _ = _oracle(db)
-    gdb, _ = _gpu(db)
+    gdb, _ = _gpu(db, layout)
     probe = np.concatenate([db.keys, H.canonical(rng.integers(0, 1 << 60, size=20000, dtype=np.uint64))])
     want = np.array([odb.lookup(int(k)) for k in probe.tolist()], dtype=np.uint32)
     got = gdb.lookup(probe)
@@ -85,11 +92,11 @@ def test_msca_exhaustive_sample():
     (15, 1500, dict(length=31)),
     (16, 1500, dict(on_target=1.0, sub_rate=0.0, n_rate=0.0)),
 ])
-def test_classify_matches_oracle(seed, n, kw):
+def test_classify_matches_oracle(seed, n, kw, layout):
     rng = np.random.default_rng(seed)
     db = H.make_db(rng, 30000, n_dup=500, n_zero=50)
     odb, osamp = _oracle(db)
-    gdb, gs = _gpu(db)
+    gdb, gs = _gpu(db, layout)
     batch = H.make_reads(rng, db, n, **kw)
     fin = _check_batch(gs, osamp, batch)
     _check_counts(gs, osamp)
@@ -106,17 +113,17 @@ def test_classify_matches_oracle(seed, n, kw):
     _check_counts(gs, osamp)
 
 
-def test_classify_without_quality_fasta_rule():
+def test_classify_without_quality_fasta_rule(layout):
     rng = np.random.default_rng(21)
     db = H.make_db(rng, 20000)
     odb, osamp = _oracle(db)
-    gdb, gs = _gpu(db)
+    gdb, gs = _gpu(db, layout)
     batch = H.make_reads(rng, db, 2500, ragged=True)
     _check_batch(gs, osamp, batch, with_qual=False)
     _check_counts(gs, osamp)
 
 
-def test_accept_u_flag():
+def test_accept_u_flag(layout):
     import kmer_id_b200 as kid
     from oracle import kor
     rng = np.random.default_rng(22)
@@ -126,17 +133,17 @@ def test_accept_u_flag():
     batch.seq[::7][batch.seq[::7] == ord("U")] = ord("u")
     for flags_o, flags_g in ((0, 0), (kor.FLAG_ACCEPT_U, kid.KID_DB_ACCEPT_U)):
         odb, osamp = _oracle(db, flags_o)
-        gdb, gs = _gpu(db, flags_g)
+        gdb, gs = _gpu(db, flags_g | layout)
         fin = _check_batch(gs, osamp, batch)
         _check_counts(gs, osamp)
         assert ((fin > 1).sum() > 100) == bool(flags_o)
 
 
-def test_displaced_entries_small_table_high_load():
+def test_displaced_entries_small_table_high_load(layout):
     """Force bucket overflow: 2^22 buckets hold 16.7 M slots; 6 M keys -> many displaced keys."""
     rng = np.random.default_rng(23)
     db = H.make_db(rng, 6_000_000)
-    gdb, gs = _gpu(db, log2_buckets=22)
+    gdb, gs = _gpu(db, layout, log2_sectors=22)
     st = gdb.stats()
     assert st["n_displaced"] > 10000
     odb, osamp = _oracle(db)
@@ -151,12 +158,12 @@ def test_displaced_entries_small_table_high_load():
     _check_counts(gs, osamp)
 
 
-def test_device_resident_entry_point_and_chunking():
+def test_device_resident_entry_point_and_chunking(layout):
     import torch
     rng = np.random.default_rng(24)
     db = H.make_db(rng, 20000)
     odb, osamp = _oracle(db)
-    gdb, gs = _gpu(db)
+    gdb, gs = _gpu(db, layout)
     batch = H.make_reads(rng, db, 5000, ragged=True)
     seq, qual = batch.padded()
     fin_o, _ = osamp.classify(batch.seq, batch.qual, batch.off)

@@ -6,6 +6,8 @@ import kmer_id_b200 as kid
 
 n_keys = int(float(sys.argv[1])) if len(sys.argv) > 1 else 108_585_519
 n_reads = int(float(sys.argv[2])) if len(sys.argv) > 2 else 4_000_000
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+log2s = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 L = 150
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(1)
@@ -13,7 +15,7 @@ keys = torch.randint(0, 1 << 60, (n_keys,), dtype=torch.int64, device=dev, gener
 taxa = torch.randint(2, 5982, (n_keys,), dtype=torch.int32, device=dev, generator=g)
 parent = np.ones(5982, np.int32)
 t0 = time.time()
-db = kid.Database(keys, taxa, parent)
+db = kid.Database(keys, taxa, parent, flags=flags, log2_sectors=log2s)
 torch.cuda.synchronize()
 print("build s", time.time() - t0, db.stats())
 del keys, taxa
