@@ -72,7 +72,7 @@ struct kid_db {
     uint2 *tree = nullptr;
     uint64_t n_distinct = 0, n_displaced = 0;
 
-    uint64_t n_slots() const { return layout == KID_LAYOUT_KEYHASH ? 4 * n_sectors : 2 * n_sectors; }
+    uint64_t n_slots() const { return layout == KID_LAYOUT_KEYHASH ? 4 * n_sectors : KID2_SLOTS_PER_SECTOR * n_sectors; }
     const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
     KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
     Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - 2), max_probe }; }
@@ -166,8 +166,9 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
 {
     if (!out) return fail(KID_EINVAL, "kid_db_build: out is NULL");
     *out = nullptr;
-    if (n_taxa < 2 || n_taxa > KID_MAX_TAXA)
-        return fail(KID_EINVAL, "kid_db_build: n_taxa %d outside [2,%d]", n_taxa, KID_MAX_TAXA);
+    const int max_taxa = (flags & KID_DB_LAYOUT_KEYHASH) ? KID_MAX_TAXA : KID2_MAX_TAXA + 1;
+    if (n_taxa < 2 || n_taxa > max_taxa)
+        return fail(KID_EINVAL, "kid_db_build: n_taxa %d outside [2,%d]", n_taxa, max_taxa);
     if (!parent) return fail(KID_EINVAL, "kid_db_build: parent is NULL");
     if (n_keys && (!keys || !taxa)) return fail(KID_EINVAL, "kid_db_build: keys/taxa NULL");
     if (n_keys >= 0xFFFFFFFFull) return fail(KID_EINVAL, "kid_db_build: more than 2^32-2 probe entries");
@@ -192,9 +193,10 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     const bool fixed = log2_sectors != 0;
     int B = log2_sectors;
     if (!fixed) {
-        // layout K: ~1 key per 4-slot sector.  layout M: ~0.8 keys per 2-slot sector (3.3 per line)
+        // layout K: ~1 key per 4-slot sector.  layout M: <= 0.45 keys per 3-slot sector, so that <1 % of
+        // lookups meet a full sector and need a second one
         B = lo;
-        const double per_sector = layout == KID_LAYOUT_KEYHASH ? 1.0 : 0.825;
+        const double per_sector = layout == KID_LAYOUT_KEYHASH ? 1.0 : 0.45;
         while (B < hi && (double)((uint64_t)1 << B) * per_sector < (double)n_keys) B++;
     }
 
@@ -260,14 +262,17 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
             db->n_displaced = st.n_displaced;
             db->max_probe = KID_MAX_DISP;
         } else {
-            const size_t n_entries = (size_t)(2 * n_sectors);
-            KID_CUDA_B(cudaMalloc(&db->entries, n_entries * sizeof(uint4)));
-            KID_CUDA_B(kid_launch_fill2(db->entries, n_entries, stream));
-            KID_CUDA_B(kid_launch_build2(db->entries, B - 2, dkeys, dtaxa, n_keys, n_taxa,
+            const size_t n_slots = (size_t)(KID2_SLOTS_PER_SECTOR * n_sectors);
+            KID_CUDA_B(cudaMalloc(&db->entries, (size_t)(2 * n_sectors) * sizeof(uint4)));
+            KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
+            KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
+            KID_CUDA_B(kid_launch_build2(db->entries, B - 2, owner, dkeys, dtaxa, n_keys, n_taxa,
                                          static_cast<Kid2BuildStatus *>(dstatus), stream));
             Kid2BuildStatus st;
             KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
             KID_CUDA_B(cudaStreamSynchronize(stream));
+            cudaFree(owner);
+            owner = nullptr;
             range_error = st.range_error;
             overflow = st.overflow;
             db->n_distinct = st.n_distinct;

@@ -26,6 +26,7 @@
 //           gcount[final]++ (:613) in a shared-memory histogram flushed once per block.
 #include "kid_kernels.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -34,7 +35,6 @@ constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
 constexpr int kWindowStarts = 448; // k-mer starts per staged window: 15 + 447 + 14 + 15 < 512
 constexpr int kCodeWords = 40; // 32 + zero padding so that halo lanes never need a bounds check
 constexpr int kValidWords = 20; // 16 + zero padding
-constexpr int kUnroll = 4;
 
 struct WarpStrip {
     uint32_t codes[kCodeWords];
@@ -42,16 +42,22 @@ struct WarpStrip {
     uint32_t kmask[kValidWords];
 };
 
+// 4 ASCII bases in one 32-bit word (first base in the low byte) -> 8 bits of 2-bit codes with the
+// first base in the top pair, and a 4-bit validity mask with the first base in the top bit.
+// Bits 2..1 of the byte are the raw code r (A 0, C 1, T/U 2, G 3); ignoring those and the case bit,
+// an A/C/G byte equals 0x41 and a T byte equals 0x41 ^ 0x11, so one xor/and and an exact
+// zero-byte test decide ACGTacgt (+Uu) for four bases at once.
 __device__ __forceinline__ void pack4(uint32_t x, bool accept_u, uint32_t &code8, uint32_t &valid4)
 {
-    const uint32_t up = x & 0xDFDFDFDFu;
-    uint32_t ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) |
-                  __vcmpeq4(up, 0x47474747u) | __vcmpeq4(up, 0x54545454u);
-    if (accept_u) ok |= __vcmpeq4(up, 0x55555555u);
-    uint32_t c = (x >> 1) & 0x03030303u; // A0 C1 T/U2 G3, then swap 2<->3 -> A0 C1 G2 T3 (:480-519)
+    const uint32_t s1 = x >> 1, s2 = x >> 2;
+    const uint32_t tflag = s2 & ~s1 & 0x01010101u; // r == 2
+    uint32_t z = ((x ^ 0x41414141u) & 0xD9D9D9D9u) ^ (tflag * 0x11u);
+    if (accept_u) z &= ~tflag; // 'U' differs from 'T' in bit 0 only (kmer_read_vf6.cpp:496-500)
+    const uint32_t nz = (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u; // 0x80 per non-zero byte
+    valid4 = ((((nz ^ 0x80808080u) >> 7) * 0x08040201u) >> 24) & 0xFu;
+    uint32_t c = s1 & 0x03030303u; // swap 2<->3 -> A0 C1 G2 T3 (:480-519)
     c ^= (c >> 1) & 0x01010101u;
     code8 = (c * 0x40100401u) >> 24;
-    valid4 = ((ok & 0x01010101u) * 0x08040201u) >> 24 & 0xFu;
 }
 
 // generic 32-positions-per-step scans (fallbacks of the trim fast path) -----------------------
@@ -96,8 +102,10 @@ __device__ __forceinline__ int scan_window_bwd(const signed char *q, int stop, i
     return lo;
 }
 
-template <bool HAS_QUAL, bool SMEM_HIST>
-__global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 3)
+// kUnroll = chunks of 32 k-mers whose sector loads are in flight together; kMinBlocks = resident
+// blocks per SM the register budget is cut for (launch bounds)
+template <bool HAS_QUAL, bool SMEM_HIST, int kUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(KID_CLASSIFY_THREADS, kMinBlocks)
 kid_classify2_kernel(const KidClassifyParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,6 +148,15 @@ kid_classify2_kernel(const KidClassifyParams p)
             const signed char *q = reinterpret_cast<const signed char *>(p.qual) + g0;
             const int qa = lane < len ? (int)q[lane] : -128;           // q[0..31]
             const int qb = lane < len ? (int)q[len - 1 - lane] : -128; // q[len-1 .. len-32]
+            // fast path (most reads): both end bases and both end windows pass -> nothing to trim
+            bool untouched = false;
+            if (len >= 6) {
+                int sa = qa + __shfl_down_sync(full, qa, 1), sb = qb + __shfl_down_sync(full, qb, 1);
+                sa += __shfl_down_sync(full, sa, 2); // lane 0: q[0]+q[1]+q[2]+q[3]
+                sb += __shfl_down_sync(full, sb, 2); // lane 0: q[len-1]+...+q[len-4]
+                untouched = __shfl_sync(full, (int)(qa >= 49 && qb >= 49 && sa - 128 >= 68 && sb - 128 >= 68), 0) != 0;
+            }
+            if (!untouched) {
             { // while (qual[start] < '1' && start < stop) start++;
                 const unsigned m = __ballot_sync(full, lane < stop && qa >= 49);
                 start = m ? __ffs(m) - 1 : scan_first_good(q, 32, stop, lane);
@@ -171,6 +188,7 @@ kid_classify2_kernel(const KidClassifyParams p)
                 else if (!mk && !unk) stop = lo;
                 else stop = scan_window_bwd(q, stop, lo, lane);
             }
+            } // !untouched
         }
         if (p.out_span && lane == 0) {
             p.out_span[2 * r] = (uint32_t)start;
@@ -296,13 +314,16 @@ kid_classify2_kernel(const KidClassifyParams p)
                     taxon[u] = 0; slotj[u] = 0;
                     if (FULL || u < nch) {
                         const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                        const bool h0 = act[u] && ea[u].x == klo && ea[u].y == khi;
-                        const bool h1 = act[u] && eb[u].x == klo && eb[u].y == khi;
-                        taxon[u] = h0 ? ea[u].z : (h1 ? eb[u].z : 0u);
-                        slotj[u] = h1 ? 1u : 0u;
-                        // full sector (both entries carry bit 63) without a match: the key may live
-                        // in a later sector
-                        const bool more = act[u] && !h0 && !h1 && (int32_t)(ea[u].y & eb[u].y) < 0;
+                        const bool h0 = ea[u].x == klo && ea[u].y == khi;
+                        const bool h1 = ea[u].z == klo && ea[u].w == khi;
+                        const bool h2 = eb[u].x == klo && eb[u].y == khi;
+                        if (act[u] && (h0 || h1 || h2)) { // rare
+                            slotj[u] = h0 ? 0u : (h1 ? 1u : 2u);
+                            taxon[u] = kid2_taxon_of(eb[u].z, eb[u].w, (int)slotj[u]);
+                        }
+                        // full sector (all three entries carry bit 63) without a match: the key may
+                        // live in a later sector
+                        const bool more = act[u] && !(h0 || h1 || h2) && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
                         again |= more ? (1u << u) : 0u;
                     }
                 }
@@ -319,17 +340,18 @@ kid_classify2_kernel(const KidClassifyParams p)
                     for (int u = 0; u < kUnroll; u++) {
                         if ((FULL || u < nch) && ((again >> u) & 1u)) {
                             const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                            const bool h0 = ea[u].x == klo && ea[u].y == khi;
-                            const bool h1 = eb[u].x == klo && eb[u].y == khi;
-                            if (h0 || h1) {
-                                taxon[u] = h0 ? ea[u].z : eb[u].z;
-                                slotj[u] = h1 ? 1u : 0u;
+                            uint32_t tx = 0;
+                            int j = 0;
+                            const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
+                            if (res > 0) {
+                                taxon[u] = tx;
+                                slotj[u] = (uint32_t)j;
                                 sec[u] = (uint32_t)(((uint64_t)sec[u] + 1) & tab.sector_mask);
-                            } else if ((int32_t)(ea[u].y & eb[u].y) < 0) { // rare: third sector and on
+                            } else if (res < 0) { // rare: third sector and on
                                 uint64_t slot = 0;
                                 taxon[u] = kid2_lookup_from(tab, sec[u], key[u], 2, slot);
-                                sec[u] = (uint32_t)(slot >> 1);
-                                slotj[u] = (uint32_t)slot & 1u;
+                                sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
+                                slotj[u] = (uint32_t)(slot % KID2_SLOTS_PER_SECTOR);
                             }
                         }
                     }
@@ -341,7 +363,7 @@ kid_classify2_kernel(const KidClassifyParams p)
                     unsigned m = __ballot_sync(full, taxon[u] > 0);
                     if (m) {
                         if (taxon[u] > 1) { // :596-603 - fire and forget, the OR is idempotent
-                            const uint64_t slot = 2 * (uint64_t)sec[u] + slotj[u];
+                            const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + slotj[u];
                             atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
                         }
                         n_hits += __popc(m);
@@ -385,11 +407,11 @@ kid_classify2_kernel(const KidClassifyParams p)
     }
 }
 
-template <bool Q, bool H>
+template <bool Q, bool H, int U, int MB>
 cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WarpStrip) * kWarpsPerBlock + (H ? (size_t)p.tree.n_taxa * 4 : 0);
-    auto kern = kid_classify2_kernel<Q, H>;
+    auto kern = kid_classify2_kernel<Q, H, U, MB>;
     cudaError_t err = cudaSuccess;
     if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -408,13 +430,33 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
     return cudaGetLastError();
 }
 
+template <int U, int MB>
+cudaError_t launch_variant(const KidClassifyParams &p, int sm_count, cudaStream_t stream)
+{
+    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
+    if (p.qual) return hist ? launch_one<true, true, U, MB>(p, sm_count, stream)
+                            : launch_one<true, false, U, MB>(p, sm_count, stream);
+    return hist ? launch_one<false, true, U, MB>(p, sm_count, stream)
+                : launch_one<false, false, U, MB>(p, sm_count, stream);
+}
+
 } // namespace
 
 cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaStream_t stream)
 {
-    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
-    if (p.qual) return hist ? launch_one<true, true>(p, sm_count, stream)
-                            : launch_one<true, false>(p, sm_count, stream);
-    return hist ? launch_one<false, true>(p, sm_count, stream)
-                : launch_one<false, false>(p, sm_count, stream);
+#ifdef KID_TUNE_VARIANTS // experiment builds only: pick the variant with KID_TUNE=<n>
+    static const int tune = getenv("KID_TUNE") ? atoi(getenv("KID_TUNE")) : 0;
+    switch (tune) {
+    case 1: return launch_variant<4, 2>(p, sm_count, stream);
+    case 2: return launch_variant<4, 3>(p, sm_count, stream);
+    case 3: return launch_variant<2, 5>(p, sm_count, stream);
+    case 4: return launch_variant<2, 3>(p, sm_count, stream);
+    case 5: return launch_variant<1, 5>(p, sm_count, stream);
+    case 6: return launch_variant<3, 3>(p, sm_count, stream);
+    default: break;
+    }
+#endif
+    // measured on B200 (tools/run_tune.sh): 2 chunks in flight at 4 blocks/SM (64 registers) beats
+    // 4 chunks at 3 blocks/SM by 27 % - the kernel is issue/latency bound, not DRAM bound
+    return launch_variant<2, 4>(p, sm_count, stream);
 }

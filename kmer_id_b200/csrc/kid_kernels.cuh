@@ -45,7 +45,7 @@ cudaError_t kid_launch_build(uint64_t *slots, int log2_buckets, uint32_t *owner,
                              const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int n_taxa,
                              KidBuildStatus *status, cudaStream_t stream);
 
-// layout M: entries must be filled with {0, 0, 0xFFFFFFFF} (aux = owner), status zeroed
+// layout M: owner (uint32 per slot, 3 per sector) must be filled with 0xFFFFFFFF, status zeroed
 struct Kid2BuildStatus {
     unsigned long long n_distinct;
     unsigned long long n_displaced; // keys outside their home sector
@@ -55,14 +55,14 @@ struct Kid2BuildStatus {
     unsigned int pad;
 };
 #define KID2_BUILD_MAX_PROBE 4096
-cudaError_t kid_launch_fill2(uint4 *entries, size_t n_entries, cudaStream_t stream);
-cudaError_t kid_launch_build2(uint4 *entries, int log2_lines, const uint64_t *keys, const uint32_t *taxa,
-                              size_t n_keys, int n_taxa, Kid2BuildStatus *status, cudaStream_t stream);
+cudaError_t kid_launch_build2(uint4 *sectors, int log2_lines, uint32_t *owner, const uint64_t *keys,
+                              const uint32_t *taxa, size_t n_keys, int n_taxa, Kid2BuildStatus *status,
+                              cudaStream_t stream);
 cudaError_t kid_launch_lookup2(const Kid2TableView &t, const uint64_t *keys, size_t n, uint32_t *out,
                                cudaStream_t stream);
 
 // ---- sample-end kernels (kid_sample.cu) ------------------------------------------------------------
-// slots: layout K = uint64 entries, layout M = 16-byte entries (taxon in the third word)
+// slots: layout K = uint64 entries, layout M = packed 32-byte sectors of 3 entries
 cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *seen, uint64_t word0,
                               uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream);
 #define KID_MAX_OR_SOURCES 16

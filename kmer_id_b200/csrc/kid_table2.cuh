@@ -11,11 +11,12 @@
 //   M(key)   = min_i c(i)                                              strand independent
 //   line     = (M * 0x9E3779B1) >> (32 - L)                            2^L lines of 128 bytes
 //   sector   = 4 * line + kid_key_sector(key)                          4 sectors per line
-//   entry    = { key | 1<<63 , taxon , 0 }  16 bytes, 2 per 32-byte sector, 8 per line
+//   sector   = 3 entries: words 0..5 = three 64-bit keys (key | 1<<63, 0 = empty), words 6..7 =
+//              three 21-bit taxa; 12 entries per 128-byte line
 // Adjacent k-mers of a read share their minimizer in runs of ~7.5, so the 32 lanes of a warp (32
 // consecutive k-mers) touch ~5 distinct lines instead of 32: ~6.5x fewer DRAM line fetches and
 // L2 requests per lookup.  Within the line the key picks the sector, so one lane still reads just
-// 32 bytes, and a genome region whose k-mers share a minimizer spreads over the line's 8 slots.
+// 32 bytes, and a genome region whose k-mers share a minimizer spreads over the line's 12 slots.
 // A key that finds its sector full moves to the next sector (linear probing in sector units);
 // sectors only ever fill up, so a lookup stops at the first sector that has an empty slot.
 // Full 60-bit keys are stored, so a match is exact by construction (no fingerprints).
@@ -29,14 +30,12 @@
 #define KID2_MIN_LOG2_LINES 10
 #define KID2_MAX_LOG2_LINES 30 /* sector indices stay below 2^32 */
 
-struct Kid2Entry {
-    uint64_t keyword; // key | KID2_OCC, 0 = empty
-    uint32_t taxon;
-    uint32_t aux;
-};
+#define KID2_SLOTS_PER_SECTOR 3
+#define KID2_TAXON_BITS 21
+#define KID2_MAX_TAXA ((1 << KID2_TAXON_BITS) - 1)
 
 struct Kid2TableView {
-    const uint4 *sectors; // 2 uint4 (= 2 entries) per sector
+    const uint4 *sectors; // 2 uint4 (= 32 bytes, 3 entries) per sector
     uint64_t sector_mask; // n_sectors - 1
     int line_shift;       // 32 - log2_lines
     int max_probe;        // longest displacement (in sectors) any key needed at build time
@@ -115,14 +114,27 @@ __device__ __forceinline__ void kid2_load_sector_if(const uint4 *p, uint4 &a, ui
                  : "l"(p), "r"(pred));
 }
 
+// taxon of entry j (0..2) of a loaded sector: three 21-bit fields in words 6 and 7
+__host__ __device__ __forceinline__ uint32_t kid2_taxon_of(uint32_t w6, uint32_t w7, int j)
+{
+    const uint64_t t = ((uint64_t)w7 << 32) | w6;
+    return (uint32_t)(t >> (KID2_TAXON_BITS * j)) & (uint32_t)KID2_MAX_TAXA;
+}
+
 // 1 = hit (taxon, slot_in_sector), 0 = final miss (an empty slot), -1 = full sector without match
 __device__ __forceinline__ int kid2_match(const uint4 &a, const uint4 &b, uint32_t want_lo,
                                           uint32_t want_hi, uint32_t &taxon, int &j)
 {
-    if (a.x == want_lo && a.y == want_hi) { taxon = a.z; j = 0; return 1; }
-    if (b.x == want_lo && b.y == want_hi) { taxon = b.z; j = 1; return 1; }
-    // occupied entries carry bit 63: both high words negative <=> sector full
-    return ((int32_t)(a.y & b.y) < 0) ? -1 : 0;
+    const bool h0 = a.x == want_lo && a.y == want_hi;
+    const bool h1 = a.z == want_lo && a.w == want_hi;
+    const bool h2 = b.x == want_lo && b.y == want_hi;
+    if (h0 || h1 || h2) {
+        j = h0 ? 0 : (h1 ? 1 : 2);
+        taxon = kid2_taxon_of(b.z, b.w, j);
+        return 1;
+    }
+    // occupied entries carry bit 63: all three high words negative <=> sector full
+    return ((int32_t)(a.y & a.w & b.y) < 0) ? -1 : 0;
 }
 
 // continue a lookup from sector `s` (used for the rare full sectors and by the diagnostic kernel)
@@ -137,7 +149,7 @@ __device__ __forceinline__ uint32_t kid2_lookup_from(const Kid2TableView &t, uin
         uint32_t taxon;
         int j;
         const int r = kid2_match(a, b, lo, hi, taxon, j);
-        if (r > 0) { slot = 2 * sec + (uint64_t)j; return taxon; }
+        if (r > 0) { slot = KID2_SLOTS_PER_SECTOR * sec + (uint64_t)j; return taxon; }
         if (r == 0) return 0;
     }
     return 0;
