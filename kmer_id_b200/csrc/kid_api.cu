@@ -66,13 +66,14 @@ struct kid_db {
     int sm_count = 148;
     int max_probe = 0;
     unsigned flags = 0;
-    uint64_t n_sectors = 0;     // 32-byte sectors (layout K: 4 slots each, layout M: 2 entries each)
+    uint64_t n_sectors = 0;     // addressable home sectors of 32 bytes (K: 4 slots each, M: 3 entries each)
+    uint64_t total_sectors = 0; // n_sectors + slack (clusters run past the last home sector, no wrap)
     uint64_t *slots = nullptr;  // layout K
     uint4 *entries = nullptr;   // layout M
     uint2 *tree = nullptr;
     uint64_t n_distinct = 0, n_displaced = 0;
 
-    uint64_t n_slots() const { return layout == KID_LAYOUT_KEYHASH ? 4 * n_sectors : KID2_SLOTS_PER_SECTOR * n_sectors; }
+    uint64_t n_slots() const { return (layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR) * total_sectors; }
     const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
     KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
     Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - 2), max_probe }; }
@@ -213,6 +214,7 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     uint64_t *tmp_keys = nullptr;
     uint32_t *tmp_taxa = nullptr, *owner = nullptr;
     void *dstatus = nullptr;
+    (void)0;
     auto cleanup_tmp = [&]() {
         cudaFree(tmp_keys); cudaFree(tmp_taxa); cudaFree(owner); cudaFree(dstatus);
         tmp_keys = nullptr; tmp_taxa = nullptr; owner = nullptr; dstatus = nullptr;
@@ -241,56 +243,46 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
 
     for (;;) {
         const uint64_t n_sectors = (uint64_t)1 << B;
-        bool range_error = false, overflow = false;
-        KID_CUDA_B(cudaMemsetAsync(dstatus, 0, 64, stream));
-        if (layout == KID_LAYOUT_KEYHASH) {
-            const size_t n_slots = (size_t)(4 * n_sectors);
-            KID_CUDA_B(cudaMalloc(&db->slots, n_slots * sizeof(uint64_t)));
-            KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
-            KID_CUDA_B(cudaMemsetAsync(db->slots, 0, n_slots * sizeof(uint64_t), stream));
-            KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
-            KID_CUDA_B(kid_launch_build(db->slots, B, owner, dkeys, dtaxa, n_keys, n_taxa,
-                                        static_cast<KidBuildStatus *>(dstatus), stream));
-            KidBuildStatus st;
-            KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
+        KidSortedBuildParams bp;
+        bp.layout = layout;
+        bp.slots_per_sector = layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR;
+        bp.n_sectors = n_sectors;
+        bp.slack_sectors = layout == KID_LAYOUT_KEYHASH ? KID1_SLACK_SECTORS : KID2_SLACK_SECTORS;
+        bp.line_shift = 32 - (B - 2);
+        bp.rem_bits = 60 - B;
+        bp.n_taxa = (uint32_t)n_taxa;
+        bp.max_taxon = layout == KID_LAYOUT_KEYHASH ? (uint32_t)KID_MAX_TAXA : (uint32_t)KID2_MAX_TAXA;
+        bp.max_disp = layout == KID_LAYOUT_KEYHASH ? (uint32_t)KID_MAX_DISP : (uint32_t)(KID2_SLACK_SECTORS - 1);
+        const uint64_t total_sectors = n_sectors + bp.slack_sectors;
+        const size_t n_slots = (size_t)(total_sectors * (uint64_t)bp.slots_per_sector);
+        Kid2BuildStatus st;
+        KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
+        KID_CUDA_B(kid_build_owner_sorted(dkeys, dtaxa, n_keys, bp, owner, static_cast<Kid2BuildStatus *>(dstatus),
+                                          &st, stream));
+        if (st.range_error)
+            return bail(fail(KID_ERANGE, "probe table: a probe names a taxon >= n_taxa (%d); the "
+                                         "reference indexes gcount[] out of bounds here", n_taxa));
+        if (!st.overflow) {
+            if (layout == KID_LAYOUT_KEYHASH) {
+                KID_CUDA_B(cudaMalloc(&db->slots, n_slots * sizeof(uint64_t)));
+                KID_CUDA_B(kid_launch_pack1(db->slots, n_slots, bp.rem_bits, owner, dkeys, dtaxa, stream));
+            } else {
+                KID_CUDA_B(cudaMalloc(&db->entries, (size_t)(2 * total_sectors) * sizeof(uint4)));
+                KID_CUDA_B(kid_launch_pack2(db->entries, (size_t)total_sectors, owner, dkeys, dtaxa, stream));
+            }
             KID_CUDA_B(cudaStreamSynchronize(stream));
-            cudaFree(owner);
-            owner = nullptr;
-            range_error = st.range_error;
-            overflow = st.overflow;
-            db->n_distinct = st.n_distinct;
-            db->n_displaced = st.n_displaced;
-            db->max_probe = KID_MAX_DISP;
-        } else {
-            const size_t n_slots = (size_t)(KID2_SLOTS_PER_SECTOR * n_sectors);
-            KID_CUDA_B(cudaMalloc(&db->entries, (size_t)(2 * n_sectors) * sizeof(uint4)));
-            KID_CUDA_B(cudaMalloc(&owner, n_slots * sizeof(uint32_t)));
-            KID_CUDA_B(cudaMemsetAsync(owner, 0xFF, n_slots * sizeof(uint32_t), stream));
-            KID_CUDA_B(kid_launch_build2(db->entries, B - 2, owner, dkeys, dtaxa, n_keys, n_taxa,
-                                         static_cast<Kid2BuildStatus *>(dstatus), stream));
-            Kid2BuildStatus st;
-            KID_CUDA_B(cudaMemcpyAsync(&st, dstatus, sizeof st, cudaMemcpyDeviceToHost, stream));
-            KID_CUDA_B(cudaStreamSynchronize(stream));
-            cudaFree(owner);
-            owner = nullptr;
-            range_error = st.range_error;
-            overflow = st.overflow;
+            db->log2_sectors = B;
+            db->n_sectors = n_sectors;
+            db->total_sectors = total_sectors;
             db->n_distinct = st.n_distinct;
             db->n_displaced = st.n_displaced;
             db->max_probe = (int)st.max_probe;
-        }
-        if (range_error)
-            return bail(fail(KID_ERANGE, "probe table: a probe names a taxon >= n_taxa (%d); the "
-                                         "reference indexes gcount[] out of bounds here", n_taxa));
-        if (!overflow) {
-            db->log2_sectors = B;
-            db->n_sectors = n_sectors;
+            cudaFree(owner);
+            owner = nullptr;
             break;
         }
-        cudaFree(db->slots);
-        cudaFree(db->entries);
-        db->slots = nullptr;
-        db->entries = nullptr;
+        cudaFree(owner);
+        owner = nullptr;
         if (fixed || B == hi)
             return bail(fail(KID_EFULL, "probe table: 2^%d sectors cannot place every key", B));
         B++;
@@ -320,7 +312,7 @@ int kid_db_stats(const kid_db *db, uint64_t *n_distinct, uint64_t *n_buckets, ui
     if (!db) return fail(KID_EINVAL, "kid_db_stats: db is NULL");
     if (n_distinct) *n_distinct = db->n_distinct;
     if (n_buckets) *n_buckets = db->n_sectors;
-    if (table_bytes) *table_bytes = db->n_sectors * 32;
+    if (table_bytes) *table_bytes = db->total_sectors * 32;
     if (n_displaced) *n_displaced = db->n_displaced;
     return KID_OK;
 }

@@ -332,7 +332,7 @@ kid_classify2_kernel(const KidClassifyParams p)
 #pragma unroll
                     for (int u = 0; u < kUnroll; u++) {
                         if (FULL || u < nch) {
-                            const uint32_t s2 = (uint32_t)(((uint64_t)sec[u] + 1) & tab.sector_mask);
+                            const uint32_t s2 = sec[u] + 1; // slack sectors follow the last home sector
                             kid2_load_sector_if(tab.sectors + 2 * (uint64_t)s2, ea[u], eb[u], (again >> u) & 1u);
                         }
                     }
@@ -346,7 +346,7 @@ kid_classify2_kernel(const KidClassifyParams p)
                             if (res > 0) {
                                 taxon[u] = tx;
                                 slotj[u] = (uint32_t)j;
-                                sec[u] = (uint32_t)(((uint64_t)sec[u] + 1) & tab.sector_mask);
+                                sec[u] = sec[u] + 1;
                             } else if (res < 0) { // rare: third sector and on
                                 uint64_t slot = 0;
                                 taxon[u] = kid2_lookup_from(tab, sec[u], key[u], 2, slot);

@@ -111,7 +111,7 @@ __device__ __forceinline__ uint32_t kid_lookup_from(const KidTableView &t, uint6
     const uint64_t home = h >> t.rem_bits;
     const uint64_t rem = h & ((1ULL << t.rem_bits) - 1ULL);
     for (int d = disp0; d <= KID_MAX_DISP; d++) {
-        const uint64_t b = (home + (uint64_t)d) & t.bucket_mask;
+        const uint64_t b = home + (uint64_t)d; // slack sectors after the last home bucket, no wrap
         uint64_t e[4];
         kid_load_bucket(t.slots + 4 * b, e);
         uint32_t taxon;

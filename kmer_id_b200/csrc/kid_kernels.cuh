@@ -33,31 +33,34 @@ extern unsigned long long g_kid_kernel_launches;
 cudaError_t kid_launch_classify(const KidClassifyParams &p, int sm_count, cudaStream_t stream);  // layout K
 cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaStream_t stream); // layout M
 
-// ---- table build (kid_build.cu) -----------------------------------------------------------------
-struct KidBuildStatus {
-    unsigned long long n_distinct;  // slots claimed
-    unsigned long long n_displaced; // claimed outside the home bucket
-    unsigned int range_error;       // some taxa[i] >= n_taxa
-    unsigned int overflow;          // some key found no slot within KID_MAX_DISP buckets
-};
-// slots must be zeroed, owner filled with 0xFFFFFFFF, status zeroed
-cudaError_t kid_launch_build(uint64_t *slots, int log2_buckets, uint32_t *owner,
-                             const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int n_taxa,
-                             KidBuildStatus *status, cudaStream_t stream);
-
-// layout M: owner (uint32 per slot, 3 per sector) must be filled with 0xFFFFFFFF, status zeroed
+// ---- table build (kid_build_sorted.cu) ----------------------------------------------------------
 struct Kid2BuildStatus {
     unsigned long long n_distinct;
     unsigned long long n_displaced; // keys outside their home sector
-    unsigned int max_probe;
-    unsigned int range_error;
-    unsigned int overflow;          // a key needed more than KID2_BUILD_MAX_PROBE sectors
+    unsigned int max_probe;         // longest displacement in sectors
+    unsigned int range_error;       // some taxa[i] >= n_taxa (or too wide for the layout)
+    unsigned int overflow;          // a key fell off the slack or exceeded max_disp
     unsigned int pad;
 };
-#define KID2_BUILD_MAX_PROBE 4096
-cudaError_t kid_launch_build2(uint4 *sectors, int log2_lines, uint32_t *owner, const uint64_t *keys,
-                              const uint32_t *taxa, size_t n_keys, int n_taxa, Kid2BuildStatus *status,
-                              cudaStream_t stream);
+struct KidSortedBuildParams {
+    int layout;            // KidLayout
+    int slots_per_sector;  // 4 (K) or 3 (M)
+    uint64_t n_sectors;    // addressable home sectors (power of two)
+    uint64_t slack_sectors; // extra sectors after the last home sector (no wrap-around)
+    int line_shift;        // layout M: 32 - log2_lines
+    int rem_bits;          // layout K: 60 - log2_sectors
+    uint32_t n_taxa, max_taxon, max_disp;
+};
+#define KID2_SLACK_SECTORS 4096
+#define KID1_SLACK_SECTORS 16
+// owner: uint32[(n_sectors + slack) * slots_per_sector]; synchronises `stream`
+cudaError_t kid_build_owner_sorted(const uint64_t *keys, const uint32_t *taxa, size_t n, const KidSortedBuildParams &p,
+                                   uint32_t *owner, Kid2BuildStatus *dstatus, Kid2BuildStatus *hstatus,
+                                   cudaStream_t stream);
+cudaError_t kid_launch_pack2(uint4 *sectors, size_t n_sectors_total, const uint32_t *owner, const uint64_t *keys,
+                             const uint32_t *taxa, cudaStream_t stream);
+cudaError_t kid_launch_pack1(uint64_t *slots, size_t n_slots_total, int rem_bits, const uint32_t *owner,
+                             const uint64_t *keys, const uint32_t *taxa, cudaStream_t stream);
 cudaError_t kid_launch_lookup2(const Kid2TableView &t, const uint64_t *keys, size_t n, uint32_t *out,
                                cudaStream_t stream);
 

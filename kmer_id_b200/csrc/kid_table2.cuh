@@ -17,8 +17,10 @@
 // consecutive k-mers) touch ~5 distinct lines instead of 32: ~6.5x fewer DRAM line fetches and
 // L2 requests per lookup.  Within the line the key picks the sector, so one lane still reads just
 // 32 bytes, and a genome region whose k-mers share a minimizer spreads over the line's 12 slots.
-// A key that finds its sector full moves to the next sector (linear probing in sector units);
-// sectors only ever fill up, so a lookup stops at the first sector that has an empty slot.
+// A key that finds its sector full lives in a following sector (linear probing in sector units,
+// built in sorted order by kid_build_sorted.cu, slack sectors instead of wrap-around); every slot
+// between a key's home and its slot is occupied, so a lookup stops at the first sector that has
+// an empty slot.
 // Full 60-bit keys are stored, so a match is exact by construction (no fingerprints).
 #pragma once
 #include <cstdint>
@@ -36,7 +38,7 @@
 
 struct Kid2TableView {
     const uint4 *sectors; // 2 uint4 (= 32 bytes, 3 entries) per sector
-    uint64_t sector_mask; // n_sectors - 1
+    uint64_t sector_mask; // n_sectors - 1 (home sectors; the table has slack sectors after them)
     int line_shift;       // 32 - log2_lines
     int max_probe;        // longest displacement (in sectors) any key needed at build time
 };
@@ -143,7 +145,7 @@ __device__ __forceinline__ uint32_t kid2_lookup_from(const Kid2TableView &t, uin
 {
     const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32) | 0x80000000u;
     for (int d = probes_done; d <= t.max_probe; d++) {
-        const uint64_t sec = (s + (uint64_t)d) & t.sector_mask;
+        const uint64_t sec = s + (uint64_t)d; // clusters run into the slack sectors, never wrap
         uint4 a, b;
         kid2_load_sector(t.sectors + 2 * sec, a, b);
         uint32_t taxon;

@@ -208,3 +208,23 @@ def test_rejects_bad_inputs():
     b = H.make_reads(rng, db, 50)
     seq, qual = b.padded()
     assert (gs.classify(seq, qual, b.off) <= 0).all()
+
+
+def test_build_is_deterministic(layout):
+    """Two builds of the same probe list must give bit-identical tables: in a multi-GPU run the seen
+    bitmaps of the replicas are OR-ed by slot index (kmer_id_b200/multi_gpu.py)."""
+    import torch
+    from kmer_id_b200 import multi_gpu
+    rng = np.random.default_rng(31)
+    db = H.make_db(rng, 3_000_000, n_dup=100000, n_zero=1000)
+    tabs = []
+    for _ in range(2):
+        gdb, _ = _gpu(db, layout, log2_sectors=22)
+        ptr, n_sectors = gdb.table_device()
+        nbytes = gdb.stats()["table_bytes"]
+        t = multi_gpu.wrap_device(ptr, nbytes // 4, "<i4", torch.device("cuda:0")).clone()
+        tabs.append((t, gdb.stats()))
+        del gdb
+    assert tabs[0][1] == tabs[1][1]
+    assert torch.equal(tabs[0][0], tabs[1][0])
+    assert tabs[0][1]["n_displaced"] > 1000
