@@ -276,7 +276,7 @@ kid_classify2_kernel(const KidClassifyParams p)
 #pragma unroll
                 for (int step = 0; step < 4; step++) {
                     const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
-                    const int src = (lane + d) & 31;
+                    const int src = lane + d; // shfl takes the source lane modulo 32
                     const bool wrap = lane + d >= 32;
                     uint32_t s[kUnroll + 1];
 #pragma unroll
@@ -292,50 +292,44 @@ kid_classify2_kernel(const KidClassifyParams p)
                             if (u == nch) cm[u] = min(cm[u], wrap ? 0xFFFFFFFFu : s[u]);
                     }
                 }
-                // LOOKUP: issue every sector load (predicated, no branches) before consuming any
+                // LOOKUP: issue every sector load before consuming any.  Inactive lanes (k-mer with an
+                // N, or past the read) read sector 0 instead of branching; their result is ignored.
                 uint4 ea[kUnroll], eb[kUnroll];
                 uint32_t sec[kUnroll]; // sector index (< 2^32: at most 2^30 lines)
-                uint32_t act[kUnroll];
+                bool act[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
-                    act[u] = 0;
+                    act[u] = false;
                     if (FULL || u < nch) {
                         const int t = delta + c + 32 * u + lane;
-                        act[u] = (strip.kmask[t >> 5] << (t & 31)) >> 31;
+                        act[u] = (int32_t)(strip.kmask[t >> 5] << (t & 31)) < 0;
                         const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
                         sec[u] = (line << 2) | kid_key_sector(key[u]);
-                        kid2_load_sector_if(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u], act[u]);
+                        kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
                     }
                 }
-                // MATCH round 1, branch free
-                uint32_t taxon[kUnroll], slotj[kUnroll], again = 0;
+                // MATCH round 1: just "hit" and "sector full without a match" per lane
+                bool hit[kUnroll];
+                uint32_t again = 0;
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
-                    taxon[u] = 0; slotj[u] = 0;
+                    hit[u] = false;
                     if (FULL || u < nch) {
                         const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                        const bool h0 = ea[u].x == klo && ea[u].y == khi;
-                        const bool h1 = ea[u].z == klo && ea[u].w == khi;
-                        const bool h2 = eb[u].x == klo && eb[u].y == khi;
-                        if (act[u] && (h0 || h1 || h2)) { // rare
-                            slotj[u] = h0 ? 0u : (h1 ? 1u : 2u);
-                            taxon[u] = kid2_taxon_of(eb[u].z, eb[u].w, (int)slotj[u]);
-                        }
-                        // full sector (all three entries carry bit 63) without a match: the key may
-                        // live in a later sector
-                        const bool more = act[u] && !(h0 || h1 || h2) && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
+                        const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
+                                       (eb[u].x == klo && eb[u].y == khi);
+                        hit[u] = act[u] && h;
+                        // all three entries carry bit 63 and none matched: the key may live further on
+                        const bool more = act[u] && !h && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
                         again |= more ? (1u << u) : 0u;
                     }
                 }
                 // MATCH round 2 for the few lanes that met a full sector: all loads first
                 if (__any_sync(full, again != 0)) {
 #pragma unroll
-                    for (int u = 0; u < kUnroll; u++) {
-                        if (FULL || u < nch) {
-                            const uint32_t s2 = sec[u] + 1; // slack sectors follow the last home sector
-                            kid2_load_sector_if(tab.sectors + 2 * (uint64_t)s2, ea[u], eb[u], (again >> u) & 1u);
-                        }
-                    }
+                    for (int u = 0; u < kUnroll; u++)
+                        if (FULL || u < nch)
+                            kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
 #pragma unroll
                     for (int u = 0; u < kUnroll; u++) {
                         if ((FULL || u < nch) && ((again >> u) & 1u)) {
@@ -344,33 +338,40 @@ kid_classify2_kernel(const KidClassifyParams p)
                             int j = 0;
                             const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
                             if (res > 0) {
-                                taxon[u] = tx;
-                                slotj[u] = (uint32_t)j;
-                                sec[u] = sec[u] + 1;
+                                hit[u] = true;
+                                sec[u] = sec[u] + 1; // slack sectors follow the last home sector
                             } else if (res < 0) { // rare: third sector and on
                                 uint64_t slot = 0;
-                                taxon[u] = kid2_lookup_from(tab, sec[u], key[u], 2, slot);
-                                sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
-                                slotj[u] = (uint32_t)(slot % KID2_SLOTS_PER_SECTOR);
+                                if (kid2_lookup_from(tab, sec[u], key[u], 2, slot)) {
+                                    hit[u] = true;
+                                    sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
+                                    kid2_load_sector(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u]);
+                                }
                             }
                         }
                     }
                 }
-                // SEEN + FOLD, strictly in position order
+                // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
                     if (!FULL && u >= nch) break; // warp-uniform
-                    unsigned m = __ballot_sync(full, taxon[u] > 0);
+                    unsigned m = __ballot_sync(full, hit[u]);
                     if (m) {
-                        if (taxon[u] > 1) { // :596-603 - fire and forget, the OR is idempotent
-                            const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + slotj[u];
-                            atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                        uint32_t taxon = 0;
+                        if (hit[u]) {
+                            const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                            int j = 0;
+                            kid2_match(ea[u], eb[u], klo, khi, taxon, j);
+                            if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
+                                const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
+                                atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                            }
                         }
                         n_hits += __popc(m);
                         do { // ordered left fold over the hits of this chunk (:588-595)
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
-                            const uint32_t tj = __shfl_sync(full, taxon[u], src);
+                            const uint32_t tj = __shfl_sync(full, taxon, src);
                             if (fin > 0) { if (tj != fin) fin = kid_msca(p.tree, tj, fin); }
                             else fin = tj;
                         } while (m);

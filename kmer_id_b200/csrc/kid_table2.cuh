@@ -56,8 +56,15 @@ __host__ __device__ __forceinline__ uint32_t kid_rc16(uint32_t x)
     y = ((y >> 8) & 0x00FF00FFu) | ((y & 0x00FF00FFu) << 8);
     y = (y >> 16) | (y << 16);
 #endif
+#ifdef __CUDA_ARCH__
+    // ~(((y >> 1) & 0x55555555) | ((y << 1) & 0xAAAAAAAA)) as ONE lop3 (LUT 0x1B = ~((a&c)|(b&~c)))
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(r) : "r"(y >> 1), "r"(y << 1));
+    return r;
+#else
     y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
     return ~y;
+#endif
 }
 
 // ordering hash of a canonical 16-mer (only its order matters; it need not be a bijection)
@@ -65,8 +72,7 @@ __host__ __device__ __forceinline__ uint32_t kid_mm_hash_canon(uint32_t x)
 {
     x *= 0x9E3779B1u;
     x ^= x >> 15;
-    x *= 0x85EBCA77u;
-    x ^= x >> 13;
+    x *= 0x85EBCA77u; // no final xor-shift: only the order matters, and the line index multiplies again
     return x;
 }
 __host__ __device__ __forceinline__ uint32_t kid_mm_hash(uint32_t fwd16)
