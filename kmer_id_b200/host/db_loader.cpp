@@ -75,7 +75,7 @@ static inline bool fast_uint(const char *&p, const char *end, uint32_t &v)
 }
 
 bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
-                      std::vector<uint32_t> &taxa)
+                      std::vector<uint32_t> &taxa, bool target_signed)
 {
     if (len > 0 && line[len - 1] == '\r') len--; // :691-692
     if (len == 0) return false;                   // :693
@@ -99,12 +99,20 @@ bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
     std::replace(l.begin(), l.end(), ',', ' ');
     std::istringstream ss(l);
     std::string sequence;
-    unsigned int target;
     int org, position, count;
     char strand;
-    if (ss >> sequence >> target >> org >> position >> strand >> count) {
-        add_windows(sequence.data(), sequence.size(), target, keys, taxa);
-        return true;
+    if (target_signed) {
+        int target;
+        if (ss >> sequence >> target >> org >> position >> strand >> count) {
+            add_windows(sequence.data(), sequence.size(), (uint32_t)target, keys, taxa);
+            return true;
+        }
+    } else {
+        unsigned int target;
+        if (ss >> sequence >> target >> org >> position >> strand >> count) {
+            add_windows(sequence.data(), sequence.size(), target, keys, taxa);
+            return true;
+        }
     }
     return false;
 }
@@ -119,7 +127,7 @@ struct Block {
 };
 } // namespace
 
-void load_probes_gz(const std::string &path, ProbeSet &out, unsigned threads)
+void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed, unsigned threads)
 {
     if (threads == 0) threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
     GzLineBlocks src(path);
@@ -144,7 +152,7 @@ void load_probes_gz(const std::string &path, ProbeSet &out, unsigned threads)
             while (p < end) {
                 const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
                 if (!eol) break;
-                b->lines += parse_probe_line(p, (size_t)(eol - p), b->keys, b->taxa);
+                b->lines += parse_probe_line(p, (size_t)(eol - p), b->keys, b->taxa, target_signed);
                 p = eol + 1;
             }
             std::vector<char>().swap(b->text);
@@ -195,6 +203,70 @@ void load_probes_gz(const std::string &path, ProbeSet &out, unsigned threads)
     cv.notify_all();
     drain(true);
     for (auto &t : pool) t.join();
+}
+
+
+namespace {
+// MurmurHash3's 64-bit finaliser: the hash the reference's table uses (kmer_read_m3.cpp:191-199)
+inline uint64_t fmix64(uint64_t k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+// insertion depth (number of probes) each entry would need in the reference's table, in file order
+template <class F>
+void replay_reference_inserts(const ProbeSet &probes, int log2_cells, F on_depth)
+{
+    const uint64_t mask = (1ULL << log2_cells) - 1;
+    std::vector<uint64_t> occupied((size_t)((mask + 1) >> 6), 0);
+    for (size_t e = 0; e < probes.keys.size(); e++) {
+        if (probes.taxa[e] == 0) continue; // value 0 leaves the cell looking empty (:248-255)
+        const uint64_t hash = fmix64(probes.keys[e]);
+        uint64_t reprobe = 0, i = 0;
+        for (;;) {
+            const uint64_t index = (hash + reprobe) & mask;
+            reprobe += ++i;
+            uint64_t &w = occupied[(size_t)(index >> 6)];
+            const uint64_t bit = 1ULL << (index & 63);
+            if (!(w & bit)) { w |= bit; break; }
+        }
+        on_depth(e, (int)i);
+    }
+}
+} // namespace
+
+size_t apply_reference_probe_cap(ProbeSet &probes, int cap, int log2_cells)
+{
+    std::vector<uint64_t> deep; // keys with at least one copy beyond the cap (practically never any)
+    replay_reference_inserts(probes, log2_cells, [&](size_t e, int depth) {
+        if (depth > cap) deep.push_back(probes.keys[e]);
+    });
+    if (deep.empty()) return 0;
+    std::sort(deep.begin(), deep.end());
+    deep.erase(std::unique(deep.begin(), deep.end()), deep.end());
+    auto is_deep = [&](uint64_t k) { return std::binary_search(deep.begin(), deep.end(), k); };
+    // depth of the FIRST copy decides: it is the one getHash meets first
+    std::vector<int> first_depth(deep.size(), 0);
+    replay_reference_inserts(probes, log2_cells, [&](size_t e, int depth) {
+        const uint64_t k = probes.keys[e];
+        if (!is_deep(k)) return;
+        const size_t j = (size_t)(std::lower_bound(deep.begin(), deep.end(), k) - deep.begin());
+        if (first_depth[j] == 0) first_depth[j] = depth;
+    });
+    size_t hidden = 0;
+    for (size_t j = 0; j < deep.size(); j++) hidden += first_depth[j] > cap;
+    for (size_t e = 0; e < probes.keys.size(); e++) {
+        const uint64_t k = probes.keys[e];
+        if (!is_deep(k)) continue;
+        const size_t j = (size_t)(std::lower_bound(deep.begin(), deep.end(), k) - deep.begin());
+        if (first_depth[j] > cap) probes.taxa[e] = 0;
+    }
+    return hidden;
 }
 
 } // namespace kidhost

@@ -19,10 +19,18 @@ struct ProbeSet {
 bool load_tree(const std::string &path, int n_taxa, std::vector<int32_t> &parent, std::string &msg);
 
 // probes gz: multi-threaded parse (one inflate thread, `threads` parser threads), order preserved.
-void load_probes_gz(const std::string &path, ProbeSet &out, unsigned threads = 0);
+// target_signed: the target column is extracted into an `int` (kmer_read_m3.cpp:847,875,
+// kmer_read_vf6.cpp) instead of an `unsigned int` (newkmer_10nx.cpp:670,697) - only odd lines differ.
+void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed = false, unsigned threads = 0);
 
 // one line (without its '\n'); appends windows to keys/taxa; returns true if the line parsed
 bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
-                      std::vector<uint32_t> &taxa);
+                      std::vector<uint32_t> &taxa, bool target_signed = false);
+
+// kmer_read_m3.cpp:42,232 - getHash gives up after MAXREPROBE = 16 probes while add_kmer (:235-264)
+// does not: a key whose FIRST inserted copy sits deeper than 16 probes in the reference's
+// 2^30-cell triangular-probing table is invisible.  Replays the reference's insertion order on an
+// occupancy bitmap and zeroes the taxon of every copy of such keys.  Returns how many keys were hidden.
+size_t apply_reference_probe_cap(ProbeSet &probes, int cap = 16, int log2_cells = 30);
 
 } // namespace kidhost

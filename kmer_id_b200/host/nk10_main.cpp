@@ -10,7 +10,7 @@
 // timings to stderr.
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
-#include "fastq_reader.hpp"
+#include "read_reader.hpp"
 
 #include <chrono>
 #include <cstdio>
@@ -52,7 +52,7 @@ struct SampleState {
 // classify one FASTQ file batch by batch; appends to _reads.txt exactly as process_read :608-614
 void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream &outread)
 {
-    FastqBatchReader reader(path, (size_t)1 << 19, (size_t)96 << 20);
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 19, (size_t)96 << 20);
     std::vector<int32_t> taxon;
     std::vector<uint32_t> span;
     for (;;) {
