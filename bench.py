@@ -179,7 +179,7 @@ def run_ours(args):
     doff = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * READ_LEN
     dout = torch.empty(n_reads, dtype=torch.int32, device=dev)
     sample = kid.Sample(db)
-    engine = multi_gpu.CudaEngine(sample, stream)
+    engine, transport = multi_gpu.make_engine(sample, stream, prefer_peer=os.environ.get("KID_PEER", "1") != "0")
     torch.cuda.synchronize()
 
     k_ev = []
@@ -193,7 +193,7 @@ def run_ours(args):
         if timed:
             b.record()
             k_ev.append((a, b))
-        return multi_gpu.sample_end(engine)
+        return multi_gpu.finish(engine)
 
     def barrier():
         if world > 1:
@@ -242,7 +242,7 @@ def run_ours(args):
         def step_e2e():
             sample.begin(stream)
             sample.classify_host(hseq, hqual, hoff, n_reads, hout, None)
-            return multi_gpu.sample_end(engine)
+            return multi_gpu.finish(engine)
 
         for _ in range(max(1, min(args.warmup, 2))):
             g2, u2 = step_e2e()
@@ -290,6 +290,9 @@ def run_ours(args):
         "lookups_per_s_whole_step": world * lookups / (ms_per_step / 1e3),
         "table": {"layout": args.layout, "bytes": st["table_bytes"], "distinct_keys": st["n_distinct"], "displaced": st["n_displaced"],
                   "build_s": build_s},
+        "sample_end": {"peer": "one fused OR+histogram kernel over NVLink-mapped peer bitmaps + 2 small all-reduces",
+                       "nccl": "all-to-all of bitmap slices + OR kernel + histogram kernel + 2 small all-reduces"}[transport]
+                      if world > 1 else "single GPU: histogram kernel",
         "hit_fraction": counters["hits"] / max(1, lookups),
         "classified_fraction": float((gcount[2:].sum()) / max(1, gcount.sum())),
     }

@@ -139,6 +139,16 @@ int kid_sample_seen_device(kid_sample *s, uint32_t **seen, uint64_t *n_words);
  * memory mapped over NVLink): dst[i] = src[0][word0+i] | ... ; dst may alias a src range. */
 int kid_seen_or_device(const kid_db *db, uint32_t *dst, const uint32_t *const *src, int n_src,
                        uint64_t word0, uint64_t n_words, void *stream);
+/* Fused form of the two calls above for peer memory: ucount_partial[t] += #slots of taxon t whose
+ * flag is set in ANY of the n_src bitmaps, for words [word0, word0+n).  The sources are read in
+ * place - with NVLink-mapped peer pointers (CUDA IPC / symmetric memory) the OR-reduction and the
+ * histogram are one kernel and no bitmap is copied or written.  n_src <= 16. */
+int kid_ucount_or_range_device(const kid_db *db, const uint32_t *const *seen_srcs, int n_src,
+                               uint64_t word0, uint64_t n_words, int32_t *ucount_partial, void *stream);
+/* Make the sample keep its seen flags in caller-owned device memory of at least n_words 32-bit
+ * words (e.g. a symmetric-memory allocation that peers can map).  The buffer is cleared by
+ * kid_sample_begin like the internal one and is not freed by the library. */
+int kid_sample_use_seen_buffer(kid_sample *s, uint32_t *buf, uint64_t n_words);
 /* ucount_partial[t] += #set flags in seen[word0 .. word0+n) whose slot holds taxon t
  * (device int32[n_taxa], NOT zeroed here).  With disjoint word ranges per rank the partial
  * histograms are additive, so a sum-all-reduce finishes the job. */

@@ -59,6 +59,8 @@ _SIGS = {
     "kid_sample_gcount_device": (_i, [_vp, C.POINTER(_vp)]),
     "kid_sample_seen_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
     "kid_seen_or_device": (_i, [_vp, _vp, C.POINTER(_vp), _i, _u64, _u64, _vp]),
+    "kid_ucount_or_range_device": (_i, [_vp, C.POINTER(_vp), _i, _u64, _u64, _vp, _vp]),
+    "kid_sample_use_seen_buffer": (_i, [_vp, _vp, _u64]),
     "kid_ucount_range_device": (_i, [_vp, _vp, _u64, _u64, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -238,6 +240,14 @@ class Sample:
     def seen_or(self, dst: int, srcs, word0: int, n_words: int, stream: int = 0):
         arr = (_vp * len(srcs))(*srcs)
         _check(lib.kid_seen_or_device(self.db._h, dst, arr, len(srcs), word0, n_words, stream or None))
+
+    def use_seen_buffer(self, ptr: int, n_words: int):
+        _check(lib.kid_sample_use_seen_buffer(self._h, ptr, n_words))
+
+    def ucount_or_range(self, srcs, word0: int, n_words: int, ucount_partial, stream: int = 0):
+        arr = (_vp * len(srcs))(*srcs)
+        _check(lib.kid_ucount_or_range_device(self.db._h, arr, len(srcs), word0, n_words,
+                                              _as_ptr(ucount_partial), stream or None))
 
     def ucount_range(self, seen: int, word0: int, n_words: int, ucount_partial, stream: int = 0):
         _check(lib.kid_ucount_range_device(self.db._h, seen, word0, n_words, _as_ptr(ucount_partial),

@@ -83,7 +83,8 @@ struct kid_db {
 struct kid_sample {
     const kid_db *db = nullptr;
     int *gcount = nullptr, *ucount = nullptr;
-    uint32_t *seen = nullptr;
+    uint32_t *seen = nullptr;      // the bitmap in use (own_seen or a caller-provided buffer)
+    uint32_t *own_seen = nullptr;  // what this object allocated
     uint64_t n_words = 0;
     unsigned long long *counters = nullptr;
     cudaEvent_t begin_ev = nullptr;
@@ -387,7 +388,8 @@ int kid_sample_create(const kid_db *db, kid_sample **out)
     s->n_words = ((n_slots / 32) + 1023) / 1024 * 1024;
     cudaError_t e = cudaMalloc(&s->gcount, sizeof(int) * (size_t)db->n_taxa);
     if (e == cudaSuccess) e = cudaMalloc(&s->ucount, sizeof(int) * (size_t)db->n_taxa);
-    if (e == cudaSuccess) e = cudaMalloc(&s->seen, sizeof(uint32_t) * s->n_words);
+    if (e == cudaSuccess) e = cudaMalloc(&s->own_seen, sizeof(uint32_t) * s->n_words);
+    s->seen = s->own_seen;
     if (e == cudaSuccess) e = cudaMalloc(&s->counters, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->begin_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -411,7 +413,7 @@ void kid_sample_free(kid_sample *s)
         cudaFree(h.seq); cudaFree(h.qual); cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
     }
     if (s->begin_ev) cudaEventDestroy(s->begin_ev);
-    cudaFree(s->gcount); cudaFree(s->ucount); cudaFree(s->seen); cudaFree(s->counters);
+    cudaFree(s->gcount); cudaFree(s->ucount); cudaFree(s->own_seen); cudaFree(s->counters);
     delete s;
 }
 
@@ -617,6 +619,32 @@ int kid_seen_or_device(const kid_db *db, uint32_t *dst, const uint32_t *const *s
     for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i < n_src ? src[i] : nullptr;
     DeviceGuard guard(db->device);
     KID_CUDA(kid_launch_seen_or(dst, l, n_src, word0, n_words, (cudaStream_t)stream));
+    return KID_OK;
+}
+
+int kid_sample_use_seen_buffer(kid_sample *s, uint32_t *buf, uint64_t n_words)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_use_seen_buffer: s is NULL");
+    if (!buf) { s->seen = s->own_seen; return KID_OK; }
+    if (n_words < s->n_words || (reinterpret_cast<uintptr_t>(buf) & 15))
+        return fail(KID_EINVAL, "kid_sample_use_seen_buffer: need >= %llu words, 16-byte aligned",
+                    (unsigned long long)s->n_words);
+    s->seen = buf;
+    return KID_OK;
+}
+
+int kid_ucount_or_range_device(const kid_db *db, const uint32_t *const *seen_srcs, int n_src, uint64_t word0,
+                               uint64_t n_words, int32_t *ucount_partial, void *stream)
+{
+    if (!db || !seen_srcs || !ucount_partial) return fail(KID_EINVAL, "kid_ucount_or_range_device: NULL argument");
+    if (n_src < 1 || n_src > KID_MAX_OR_SOURCES)
+        return fail(KID_EINVAL, "kid_ucount_or_range_device: n_src %d outside [1,%d]", n_src, KID_MAX_OR_SOURCES);
+    if ((word0 | n_words) & 3) return fail(KID_EINVAL, "kid_ucount_or_range_device: range must be multiples of 4 words");
+    KidPtrList l;
+    for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i < n_src ? seen_srcs[i] : nullptr;
+    DeviceGuard guard(db->device);
+    KID_CUDA(kid_launch_ucount_or(db->table_ptr(), db->layout, l, n_src, word0, n_words, ucount_partial, db->n_taxa,
+                                  (cudaStream_t)stream));
     return KID_OK;
 }
 

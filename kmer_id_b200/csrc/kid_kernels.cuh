@@ -72,6 +72,9 @@ cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *see
 struct KidPtrList {
     const uint32_t *p[KID_MAX_OR_SOURCES];
 };
+// fused OR over n_src bitmaps + histogram (sources may be peer-mapped)
+cudaError_t kid_launch_ucount_or(const void *slots, int layout, const KidPtrList &src, int n_src, uint64_t word0,
+                                 uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream);
 cudaError_t kid_launch_seen_or(uint32_t *dst, const KidPtrList &src, int n_src, uint64_t word0,
                                uint64_t n_words, cudaStream_t stream);
 cudaError_t kid_launch_lookup(const KidTableView &t, const uint64_t *keys, size_t n, uint32_t *out,

@@ -7,14 +7,24 @@
 
 namespace {
 
-template <int LAYOUT>
+// N_SRC == 0: one local bitmap (src.p[0]); otherwise OR of n_src bitmaps, possibly peer memory
+template <int LAYOUT, bool MULTI>
 __global__ void __launch_bounds__(256)
-kid_ucount_kernel(const void *__restrict__ slots_, const uint4 *__restrict__ seen4,
+kid_ucount_kernel(const void *__restrict__ slots_, const KidPtrList src, int n_src,
                   uint64_t quad0, uint64_t n_quads, int *ucount, int n_taxa)
 {
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
          q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(seen4 + quad0 + q);
+        uint4 v;
+        if (!MULTI) {
+            v = __ldg(reinterpret_cast<const uint4 *>(src.p[0]) + quad0 + q);
+        } else {
+            v = make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < n_src; k++) { // peer reads go over NVLink; plain loads, not __ldg
+                const uint4 t = reinterpret_cast<const uint4 *>(src.p[k])[quad0 + q];
+                v.x |= t.x; v.y |= t.y; v.z |= t.z; v.w |= t.w;
+            }
+        }
         if ((v.x | v.y | v.z | v.w) == 0) continue;
         const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
@@ -93,12 +103,28 @@ cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *see
                               uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
+    KidPtrList l;
+    for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i == 0 ? seen : nullptr;
     if (layout == KID_LAYOUT_KEYHASH)
-        kid_ucount_kernel<KID_LAYOUT_KEYHASH><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+        kid_ucount_kernel<KID_LAYOUT_KEYHASH, false><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, l, 1, word0 / 4, n_words / 4, ucount, n_taxa);
     else
-        kid_ucount_kernel<KID_LAYOUT_MINIMIZER><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, reinterpret_cast<const uint4 *>(seen), word0 / 4, n_words / 4, ucount, n_taxa);
+        kid_ucount_kernel<KID_LAYOUT_MINIMIZER, false><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, l, 1, word0 / 4, n_words / 4, ucount, n_taxa);
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_ucount_or(const void *slots, int layout, const KidPtrList &src, int n_src, uint64_t word0,
+                                 uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream)
+{
+    if (n_words == 0) return cudaSuccess;
+    if (layout == KID_LAYOUT_KEYHASH)
+        kid_ucount_kernel<KID_LAYOUT_KEYHASH, true><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
+    else
+        kid_ucount_kernel<KID_LAYOUT_MINIMIZER, true><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
+            slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
     KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }

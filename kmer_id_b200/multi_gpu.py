@@ -10,6 +10,10 @@ reads are sharded over ranks:
   into its own bitmap and histograms that range only.  The ranges are disjoint, so the partial
   histograms ARE additive and a second small sum all-reduce finishes ucount.
 
+Two transports for the bitmap exchange: NCCL all-to-all + kid_seen_or_kernel (sample_end), or - when
+the ranks can map each other's memory - symmetric memory and ONE fused OR+histogram kernel that
+reads the peers' bitmaps over NVLink in place (sample_end_peer).
+
 The orchestration is written against a tiny "engine" interface so that the same code runs on CPU
 tensors under gloo in tests/test_multi_rank_cpu.py and on the CUDA kernels under NCCL.
 """
@@ -58,6 +62,55 @@ class CudaEngine:
 
     def ucount_range(self, word0: int, n_words: int, partial: torch.Tensor):
         self.sample.ucount_range(self._seen_ptr, word0, n_words, partial, self.stream)
+
+
+class PeerEngine(CudaEngine):
+    """Seen bitmap in symmetric memory: every rank maps every peer's bitmap over NVLink, so the
+    sample-end OR-reduction and the per-taxon histogram are ONE kernel reading peer memory in place
+    (kid_ucount_or_range_device) - no all-to-all, no staging copy, nothing written back."""
+
+    def __init__(self, sample, stream: int = 0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        super().__init__(sample, stream)
+        group = group or dist.group.WORLD
+        self.buf = symm_mem.empty(self.n_words, dtype=torch.int32, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.peer_ptrs) == dist.get_world_size(group)
+        sample.use_seen_buffer(self.buf.data_ptr(), self.n_words)
+        self.seen = self.buf
+        self._seen_ptr = self.buf.data_ptr()
+        sample.begin(stream)  # the new buffer starts cleared
+
+
+def sample_end_peer(engine: PeerEngine, group=None):
+    """(gcount, ucount) through peer memory; identical on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert engine.n_words % (4 * world) == 0
+    sw = engine.n_words // world
+    partial = engine.new_partial()
+    engine.hdl.barrier(channel=0)  # every rank's classify kernels have finished writing seen bits
+    engine.sample.ucount_or_range(engine.peer_ptrs, rank * sw, sw, partial, engine.stream)
+    engine.hdl.barrier(channel=1)  # peers are done reading this bitmap before the next begin() clears it
+    dist.all_reduce(engine.gcount, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return engine.gcount.cpu().numpy().copy(), partial.cpu().numpy()
+
+
+def make_engine(sample, stream: int = 0, group=None, prefer_peer: bool = True):
+    """PeerEngine when the ranks can map each other's memory, else the NCCL all-to-all engine."""
+    if prefer_peer and dist.is_initialized() and dist.get_world_size(group) > 1:
+        try:
+            return PeerEngine(sample, stream, group), "peer"
+        except Exception as e:  # no P2P / symmetric memory on this box
+            import sys
+            print(f"kmer_id_b200.multi_gpu: peer memory unavailable ({type(e).__name__}: {e}); using NCCL all-to-all",
+                  file=sys.stderr)
+    return CudaEngine(sample, stream), "nccl"
+
+
+def finish(engine, group=None):
+    return sample_end_peer(engine, group) if isinstance(engine, PeerEngine) else sample_end(engine, group)
 
 
 def sample_end(engine, group=None):

@@ -27,9 +27,12 @@ def main():
     keys, taxa = wl.db_host()
     n_per = 30000
     stream = torch.cuda.current_stream().cuda_stream
-    for layout in (0, kid.KID_DB_LAYOUT_KEYHASH):
+    for layout, peer in ((0, False), (kid.KID_DB_LAYOUT_KEYHASH, False), (0, True)):
         db = kid.Database(keys, taxa, parent, device=local, flags=layout)
         s = kid.Sample(db)
+        engine, transport = multi_gpu.make_engine(s, stream, prefer_peer=peer)
+        if peer and rank == 0:
+            print("transport for the peer case:", transport)
         seq, qual = wl.reads_host(rank * n_per, n_per)
         # every rank also sees the same first 2000 reads: their k-mers must count once in ucount
         cs, cq = wl.reads_host(10_000_000, 2000)
@@ -39,7 +42,7 @@ def main():
         off = wl.offsets(n)
         s.begin(stream)
         out = s.classify(seq, qual, off)
-        g, u = multi_gpu.sample_end(multi_gpu.CudaEngine(s, stream))
+        g, u = multi_gpu.finish(engine)
         # oracle over the union of all shards (each rank computes it; small)
         odb = kor.OracleDB(wl.n_taxa)
         odb.set_parents(parent)
@@ -55,7 +58,7 @@ def main():
         assert np.array_equal(g, os_.gcount), f"rank {rank}: gcount differs after all-reduce"
         assert np.array_equal(u, os_.ucount), f"rank {rank}: ucount differs after OR-reduce"
         assert u.sum() > 1000
-        del s, db
+        del engine, s, db
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity ok on {world} ranks (both layouts)")
