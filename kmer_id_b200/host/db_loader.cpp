@@ -10,6 +10,9 @@
 #include <sstream>
 #include <thread>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace kidhost {
 
 bool load_tree(const std::string &path, int n_taxa, std::vector<int32_t> &parent, std::string &msg)
@@ -205,6 +208,66 @@ void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed, 
     for (auto &t : pool) t.join();
 }
 
+
+namespace {
+struct CacheHeader {
+    char magic[8];       // "KIDCACH1"
+    uint64_t src_size;   // st_size of the text file
+    int64_t src_mtime_ns;
+    uint64_t n_entries;
+    int64_t lines_parsed;
+    uint32_t target_signed;
+    uint32_t reserved;
+};
+} // namespace
+
+bool load_probes_cached(const std::string &path, ProbeSet &out, bool target_signed)
+{
+    struct stat st;
+    const bool have_src = stat(path.c_str(), &st) == 0;
+    const std::string cpath = path + ".kidcache";
+    const bool allow = getenv("KID_NO_CACHE") == nullptr;
+    if (have_src && allow) {
+        if (FILE *f = fopen(cpath.c_str(), "rb")) {
+            CacheHeader h;
+            bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "KIDCACH1", 8) == 0 &&
+                      h.src_size == (uint64_t)st.st_size &&
+                      h.src_mtime_ns == (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec &&
+                      h.target_signed == (uint32_t)target_signed;
+            if (ok) {
+                out.keys.resize((size_t)h.n_entries);
+                out.taxa.resize((size_t)h.n_entries);
+                ok = fread(out.keys.data(), 8, out.keys.size(), f) == out.keys.size() &&
+                     fread(out.taxa.data(), 4, out.taxa.size(), f) == out.taxa.size();
+                out.lines_parsed = h.lines_parsed;
+            }
+            fclose(f);
+            if (ok) return true;
+            out.keys.clear();
+            out.taxa.clear();
+            out.lines_parsed = 0;
+        }
+    }
+    load_probes_gz(path, out, target_signed);
+    if (have_src && allow) {
+        const std::string tmp = cpath + ".tmp" + std::to_string((long)getpid());
+        if (FILE *f = fopen(tmp.c_str(), "wb")) {
+            CacheHeader h;
+            memset(&h, 0, sizeof h);
+            memcpy(h.magic, "KIDCACH1", 8);
+            h.src_size = (uint64_t)st.st_size;
+            h.src_mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
+            h.n_entries = out.keys.size();
+            h.lines_parsed = out.lines_parsed;
+            h.target_signed = (uint32_t)target_signed;
+            const bool ok = fwrite(&h, sizeof h, 1, f) == 1 &&
+                            fwrite(out.keys.data(), 8, out.keys.size(), f) == out.keys.size() &&
+                            fwrite(out.taxa.data(), 4, out.taxa.size(), f) == out.taxa.size();
+            if (fclose(f) != 0 || !ok || rename(tmp.c_str(), cpath.c_str()) != 0) remove(tmp.c_str());
+        }
+    }
+    return false;
+}
 
 namespace {
 // MurmurHash3's 64-bit finaliser: the hash the reference's table uses (kmer_read_m3.cpp:191-199)

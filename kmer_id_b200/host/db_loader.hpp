@@ -27,6 +27,12 @@ void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed =
 bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
                       std::vector<uint32_t> &taxa, bool target_signed = false);
 
+// Binary cache of a parsed probe file: `<path>.kidcache` holds the (keys, taxa)
+// arrays and the parsed-line count, stamped with the size and mtime of the text file it came from.
+// load_probes_cached() uses it when the stamp matches and otherwise parses `path` and (unless
+// KID_NO_CACHE is set or the directory is read-only) writes it.  Returns true if the cache was used.
+bool load_probes_cached(const std::string &path, ProbeSet &out, bool target_signed = false);
+
 // kmer_read_m3.cpp:42,232 - getHash gives up after MAXREPROBE = 16 probes while add_kmer (:235-264)
 // does not: a key whose FIRST inserted copy sits deeper than 16 probes in the reference's
 // 2^30-cell triangular-probing table is invisible.  Replays the reference's insertion order on an

@@ -129,7 +129,7 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl;
 
     ProbeSet probes;
-    load_probes_gz(pname, probes, /*target_signed=*/true);
+    load_probes_cached(pname, probes, /*target_signed=*/true);
     std::cout << probes.lines_parsed << " kmers loaded" << std::endl; // :1066
     if (probes.lines_parsed < 2) exit(1);                              // :1067
     // KID_REF_LOG2_CELLS: test hook - size of the reference table being replayed (MAXHASH, :41)

@@ -173,7 +173,7 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl;
 
     ProbeSet probes;
-    load_probes_gz(pname, probes, /*target_signed=*/false);
+    load_probes_cached(pname, probes, /*target_signed=*/false);
     std::cout << probes.lines_parsed << " kmers loaded" << std::endl;
     kid_db *db = nullptr;
     if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), num_targ, device,

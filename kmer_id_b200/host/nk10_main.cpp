@@ -7,7 +7,8 @@
 // libkmerid_b200.so (include/kmer_id.h); there is no CPU classification path in this program.
 //
 // Extras that do not change the contract: KID_DEVICE=<n> picks the GPU, KID_STATS=1 prints phase
-// timings to stderr.
+// timings to stderr, and the parsed probe list is cached next to probes10.txt.gz as
+// probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
 #include "read_reader.hpp"
@@ -101,7 +102,7 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl; // :984
 
     ProbeSet probes;
-    load_probes_gz(pname, probes);
+    const bool cached = load_probes_cached(pname, probes);
     const double t1 = now();
     kid_db *db = nullptr;
     if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), MAXTAR,
@@ -160,7 +161,9 @@ int main(int argc, char *argv[])
         }
     }
     if (stats)
-        fprintf(stderr, "[nk10] parse db %.3f s, build table %.3f s, total %.3f s\n", t1 - t0, t2 - t1, now() - t0);
+        fprintf(stderr, "[nk10] %s db %.3f s, build table %.3f s, total %.3f s\n", cached ? "cached" : "parse", t1 - t0,
+                t2 - t1, now() - t0);
+    (void)cached;
     kid_sample_free(smp);
     kid_db_free(db);
     return 0;

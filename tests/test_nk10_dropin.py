@@ -88,3 +88,33 @@ def test_parser_quirks_two_samples(tmp_path):
     H.write_fastq_gz(os.path.join(fq, "sampB_R1_tr.fastq.gz"), b, final_newline=False)
     H.write_fastq_gz(os.path.join(fq, "sampB_R2_tr.fastq.gz"), c)
     _run_both(work, fq)
+
+
+@pytest.mark.skipif(NK_REF is None, reason="oracle/_ref/nk10_small not built")
+def test_probe_cache_round_trip(tmp_path):
+    """Second run uses probes10.txt.gz.kidcache; touching the text file invalidates it."""
+    rng = np.random.default_rng(3004)
+    db = H.make_db(rng, 3000, n_dup=50, n_zero=10)
+    work = str(tmp_path)
+    fq = os.path.join(work, "fq")
+    os.makedirs(fq)
+    H.make_bact10_dir(work, db)
+    a = H.make_reads(rng, db, 400)
+    H.write_fastq_gz(os.path.join(fq, "c_R1_tr.fastq.gz"), a)
+    H.write_fastq_gz(os.path.join(fq, "c_R2_tr.fastq.gz"), a)
+    cache = os.path.join(work, "bact10", "probes10.txt.gz.kidcache")
+    r1 = H.run_nk10(NK_GPU, work, fq)
+    assert r1.returncode == 0 and os.path.exists(cache)
+    res1 = open(os.path.join(fq, "c_result.txt"), "rb").read()
+    env = dict(os.environ, KID_STATS="1")
+    r2 = subprocess.run([NK_GPU, fq + "/"], cwd=work, capture_output=True, env=env)
+    assert r2.returncode == 0 and b"cached db" in r2.stderr and r2.stdout == r1.stdout
+    assert open(os.path.join(fq, "c_result.txt"), "rb").read() == res1
+    # a different probe file of the same name must not be served from the stale cache
+    db2 = H.make_db(rng, 3100)
+    H.write_probes_gz(os.path.join(work, "bact10", "probes10.txt.gz"), db2)
+    r3 = subprocess.run([NK_GPU, fq + "/"], cwd=work, capture_output=True, env=env)
+    assert r3.returncode == 0 and b"parse db" in r3.stderr
+    assert b"3100 kmers loaded" in r3.stdout
+    ref = H.run_nk10(NK_REF, work, fq)
+    assert ref.stdout == r3.stdout
