@@ -228,3 +228,29 @@ def test_build_is_deterministic(layout):
     assert tabs[0][1] == tabs[1][1]
     assert torch.equal(tabs[0][0], tabs[1][0])
     assert tabs[0][1]["n_displaced"] > 1000
+
+
+def test_msca_deep_tree():
+    """kid_msca on a deep random tree (the shipped trees are at most 6 deep) against the oracle."""
+    import kmer_id_b200 as kid
+    from oracle import kor
+    rng = np.random.default_rng(61)
+    n = 400
+    parent = np.ones(n, np.int32)
+    for v in range(2, n):  # random recursive tree with a long spine: depth well beyond 7
+        parent[v] = v - 1 if v < 40 else int(rng.integers(1, v))
+    odb = kor.OracleDB(n)
+    odb.set_parents(parent)
+    gdb = kid.Database(np.zeros(0, np.uint64), np.zeros(0, np.uint32), parent)
+    x = rng.integers(1, n, size=20000).astype(np.int32)
+    y = rng.integers(1, n, size=20000).astype(np.int32)
+    want = np.array([odb.msca(int(a), int(b)) for a, b in zip(x, y)], dtype=np.int32)
+    assert np.array_equal(want, gdb.msca(x, y))
+    # and a read-level check: hits of a deep lineage folded in order
+    keys = H.canonical(rng.integers(0, 1 << 60, size=3000, dtype=np.uint64))
+    db = H.SynthDB(keys=keys, taxa=rng.integers(2, n, size=3000).astype(np.uint32), parent=parent)
+    o2, osamp = _oracle(db)
+    g2, gs = _gpu(db)
+    batch = H.make_reads(rng, db, 1500)
+    _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
