@@ -5,8 +5,12 @@
 //
 // One warp owns one read at a time (persistent grid, warp-strided reads); lane j of chunk c owns
 // the k-mer that starts at base 32c+j.
-//   LOAD    as soon as the read's offsets are known the warp issues, together, the coalesced
-//           128-bit loads of its bases and two 32-byte loads of its first/last quality bytes.
+//   GROUP   a warp takes kGroup (3) consecutive reads at a time; when they fit one 512-base window
+//           (always for 150-bp reads) they are loaded, packed and masked ONCE, which cuts the
+//           per-read prologue by ~2/3.  Longer reads take the one-read-at-a-time path (windows of
+//           448 k-mer starts).
+//   LOAD    as soon as the offsets are known the warp issues, together, the coalesced 128-bit
+//           loads of the bases and 32-byte loads of every read's first/last quality bytes.
 //   TRIM    the four `while` loops of process_qual (:727-753) are "first/last position with a
 //           property" searches; the common case is answered from the two preloaded quality
 //           registers with ballots and shuffles, the rest by a 32-positions-per-step scan.
@@ -33,13 +37,14 @@ namespace {
 
 constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
 constexpr int kWindowStarts = 448; // k-mer starts per staged window: 15 + 447 + 14 + 15 < 512
-constexpr int kCodeWords = 40; // 32 + zero padding so that halo lanes never need a bounds check
+constexpr int kCodeWords = 44; // 32 + zero padding so that halo lanes never need a bounds check
 constexpr int kValidWords = 20; // 16 + zero padding
 
 struct WarpStrip {
     uint32_t codes[kCodeWords];
     uint32_t valid[kValidWords];
     uint32_t kmask[kValidWords];
+    int meta[12]; // grouped path: {start, stop, offset in the strip} of each read of the group
 };
 
 // 4 ASCII bases in one 32-bit word (first base in the low byte) -> 8 bits of 2-bit codes with the
@@ -102,6 +107,230 @@ __device__ __forceinline__ int scan_window_bwd(const signed char *q, int stop, i
     return lo;
 }
 
+constexpr int kGroup = 3;          // consecutive reads a warp stages together
+constexpr int kGroupMaxSpan = 496; // delta + bytes of the whole group must stay inside the window
+
+// ---- TRIM (:724-753) from the two preloaded quality registers qa = q[lane], qb = q[len-1-lane]
+__device__ __forceinline__ void trim_read(const signed char *q, int len, int qa, int qb, int lane, int &start,
+                                          int &stop)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    start = 0;
+    stop = len - 1;
+    if (len <= 0) return;
+    // fast path (most reads): both end bases and both end windows pass -> nothing to trim
+    if (len >= 6) {
+        int sa = qa + __shfl_down_sync(full, qa, 1), sb = qb + __shfl_down_sync(full, qb, 1);
+        sa += __shfl_down_sync(full, sa, 2); // lane 0: q[0]+q[1]+q[2]+q[3]
+        sb += __shfl_down_sync(full, sb, 2); // lane 0: q[len-1]+...+q[len-4]
+        if (__shfl_sync(full, (int)(qa >= 49 && qb >= 49 && sa - 128 >= 68 && sb - 128 >= 68), 0)) return;
+    }
+    { // while (qual[start] < '1' && start < stop) start++;
+        const unsigned m = __ballot_sync(full, lane < stop && qa >= 49);
+        start = m ? __ffs(m) - 1 : scan_first_good(q, 32, stop, lane);
+    }
+    { // while (qual[stop] < '1' && stop > start) stop--;
+        const unsigned m = __ballot_sync(full, len - 1 - lane > start && qb >= 49);
+        stop = m ? len - 1 - (__ffs(m) - 1) : scan_last_good(q, len - 33, start, lane);
+    }
+    if (start < stop - 4) { // leading 4-base window slides right while sum(q-32) < 68
+        const int lim = stop - 4, s = start + lane;
+        const int w = __shfl_sync(full, qa, s & 31) + __shfl_sync(full, qa, (s + 1) & 31) +
+                      __shfl_sync(full, qa, (s + 2) & 31) + __shfl_sync(full, qa, (s + 3) & 31);
+        const bool known = s + 3 < 32;
+        const unsigned mk = __ballot_sync(full, known && s < lim && w - 128 >= 68);
+        const unsigned unk = __ballot_sync(full, !known && s < lim);
+        if (mk && (!unk || __ffs(mk) < __ffs(unk))) start += __ffs(mk) - 1;
+        else if (!mk && !unk) start = lim;
+        else start = scan_window_fwd(q, start, lim, lane);
+    }
+    if (start < stop - 4) { // trailing window slides left
+        const int lo = start + 4, t = stop - lane;
+        const int idx = len - 1 - t; // lane of qb that holds q[t]
+        const int w = __shfl_sync(full, qb, idx & 31) + __shfl_sync(full, qb, (idx + 1) & 31) +
+                      __shfl_sync(full, qb, (idx + 2) & 31) + __shfl_sync(full, qb, (idx + 3) & 31);
+        const bool known = idx + 3 < 32;
+        const unsigned mk = __ballot_sync(full, known && t > lo && w - 128 >= 68);
+        const unsigned unk = __ballot_sync(full, !known && t > lo);
+        if (mk && (!unk || __ffs(mk) < __ffs(unk))) stop -= __ffs(mk) - 1;
+        else if (!mk && !unk) stop = lo;
+        else stop = scan_window_bwd(q, stop, lo, lane);
+    }
+}
+
+// ---- STAGE one 512-base window: 2-bit codes, ACGT validity bits and the "a run of 30 valid bases
+// starts here" mask (bit 31 - t%32 of word t/32; the read's own range is applied by the caller)
+__device__ __forceinline__ void stage_window(WarpStrip &strip, const uint4 &v, bool accept_u, int lane)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    __syncwarp();
+    uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
+    pack4(v.x, accept_u, c0, v0);
+    pack4(v.y, accept_u, c1, v1);
+    pack4(v.z, accept_u, c2, v2);
+    pack4(v.w, accept_u, c3, v3);
+    strip.codes[lane] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    const uint32_t v16 = (v0 << 12) | (v1 << 8) | (v2 << 4) | v3;
+    const uint32_t nb = __shfl_down_sync(full, v16, 1);
+    if ((lane & 1) == 0) strip.valid[lane >> 1] = (v16 << 16) | nb;
+    __syncwarp();
+    const int l16 = lane & 15;
+    uint64_t x = ((uint64_t)strip.valid[l16] << 32) | strip.valid[l16 + 1];
+    x &= x << 1; x &= x << 2; x &= x << 4; x &= x << 8; // runs of 16 valid bases
+    x &= x << 14;                                       // runs of 30 (cpos == KSIZE, :526)
+    if (lane < 16) strip.kmask[lane] = (uint32_t)(x >> 32);
+    __syncwarp();
+}
+
+// ---- KEYS .. FOLD over the k-mers that start at window positions [first, last]; the k-mer that
+// starts at window position j has its first base at staged index tbase + j
+template <int kUnroll>
+__device__ __forceinline__ void scan_kmers(const KidClassifyParams &p, const Kid2TableView &tab, const WarpStrip &strip,
+                                           int tbase, int first, int last, int lane, uint32_t &fin,
+                                           unsigned long long &n_lookups, unsigned long long &n_hits)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    auto blockN = [&](int c, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        // chunks (of 32 k-mers) this iteration has; FULL == all of them, known at compile time
+        const int nch = FULL ? kUnroll : min(kUnroll, (last - c + 32) >> 5);
+        uint32_t cm[kUnroll + 1]; // 16-mer hashes -> sliding minima
+        uint64_t key[kUnroll];
+        // KEYS
+#pragma unroll
+        for (int u = 0; u <= kUnroll; u++) {
+            cm[u] = 0xFFFFFFFFu;
+            if (FULL || u <= nch) { // chunk nch is the 14-lane halo of chunk nch-1
+                const int t = tbase + c + 32 * u + lane; // staged index of this lane's base
+                const int w = t >> 4, sh = (t & 15) * 2;
+                const uint32_t w0 = strip.codes[w], w1 = strip.codes[w + 1];
+                const uint32_t hi = __funnelshift_l(w1, w0, sh);
+                const uint32_t rc = kid_rc16(hi);
+                cm[u] = kid_mm_hash_canon(min(hi, rc));
+                if (u < kUnroll) {
+                    // forward key = first 30 of the 32 bases at this position; the reverse complement
+                    // of 32 bases is rc16(low half) : rc16(high half) and its low 60 bits are the
+                    // reverse complement of the first 30 bases
+                    const uint32_t lo = __funnelshift_l(strip.codes[w + 2], w1, sh);
+                    const uint64_t kf = (((uint64_t)hi << 32) | lo) >> 4;
+                    const uint64_t kr = (((uint64_t)kid_rc16(lo) << 32) | rc) & KID_MASK60;
+                    key[u] = kf < kr ? kf : kr; // :528
+                }
+            }
+        }
+        // MINIM: window minimum over 15 consecutive positions (1 + 2 + 4 + 7 doubling)
+#pragma unroll
+        for (int step = 0; step < 4; step++) {
+            const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
+            const int src = lane + d; // shfl takes the source lane modulo 32
+            const bool wrap = lane + d >= 32;
+            uint32_t s[kUnroll + 1];
+#pragma unroll
+            for (int u = 0; u <= kUnroll; u++)
+                if (FULL || u <= nch) s[u] = __shfl_sync(full, cm[u], src);
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++)
+                if (FULL || u < nch) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
+            if (FULL) cm[kUnroll] = min(cm[kUnroll], wrap ? 0xFFFFFFFFu : s[kUnroll]);
+            else {
+#pragma unroll
+                for (int u = 1; u < kUnroll; u++)
+                    if (u == nch) cm[u] = min(cm[u], wrap ? 0xFFFFFFFFu : s[u]);
+            }
+        }
+        // LOOKUP: issue every sector load before consuming any.  Inactive lanes (k-mer with an N, or
+        // outside the read) read sector 0 instead of branching; their result is ignored.
+        uint4 ea[kUnroll], eb[kUnroll];
+        uint32_t sec[kUnroll]; // sector index (< 2^32: at most 2^30 lines)
+        bool act[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            act[u] = false;
+            if (FULL || u < nch) {
+                const int j = c + 32 * u + lane, t = tbase + j;
+                act[u] = (int32_t)(strip.kmask[t >> 5] << (t & 31)) < 0 && j >= first && j <= last;
+                n_lookups += __popc(__ballot_sync(full, act[u])); // each is one getHash call (:529)
+                const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
+                sec[u] = (line << 2) | kid_key_sector(key[u]);
+                kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
+            }
+        }
+        // MATCH round 1: just "hit" and "sector full without a match" per lane
+        bool hit[kUnroll];
+        uint32_t again = 0;
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            hit[u] = false;
+            if (FULL || u < nch) {
+                const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
+                               (eb[u].x == klo && eb[u].y == khi);
+                hit[u] = act[u] && h;
+                // all three entries carry bit 63 and none matched: the key may live further on
+                const bool more = act[u] && !h && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
+                again |= more ? (1u << u) : 0u;
+            }
+        }
+        // MATCH round 2 for the few lanes that met a full sector: all loads first
+        if (__any_sync(full, again != 0)) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++)
+                if (FULL || u < nch)
+                    kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                if ((FULL || u < nch) && ((again >> u) & 1u)) {
+                    const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                    uint32_t tx = 0;
+                    int j = 0;
+                    const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
+                    if (res > 0) {
+                        hit[u] = true;
+                        sec[u] = sec[u] + 1; // slack sectors follow the last home sector
+                    } else if (res < 0) { // rare: third sector and on
+                        uint64_t slot = 0;
+                        if (kid2_lookup_from(tab, sec[u], key[u], 2, slot)) {
+                            hit[u] = true;
+                            sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
+                            kid2_load_sector(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u]);
+                        }
+                    }
+                }
+            }
+        }
+        // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            if (!FULL && u >= nch) break; // warp-uniform
+            unsigned m = __ballot_sync(full, hit[u]);
+            if (m) {
+                uint32_t taxon = 0;
+                if (hit[u]) {
+                    const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                    int j = 0;
+                    kid2_match(ea[u], eb[u], klo, khi, taxon, j);
+                    if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
+                        const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
+                        atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                    }
+                }
+                n_hits += __popc(m);
+                do { // ordered left fold over the hits of this chunk (:588-595)
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t tj = __shfl_sync(full, taxon, src);
+                    if (fin > 0) { if (tj != fin) fin = kid_msca(p.tree, tj, fin); }
+                    else fin = tj;
+                } while (m);
+            }
+        }
+    };
+    for (int c = (first / 32) * 32; c <= last; c += 32 * kUnroll) {
+        if (last - c >= 32 * (kUnroll - 1)) blockN(c, std::true_type{});
+        else blockN(c, std::false_type{});
+    }
+}
+
 // kUnroll = chunks of 32 k-mers whose sector loads are in flight together; kMinBlocks = resident
 // blocks per SM the register budget is cut for (launch bounds)
 template <bool HAS_QUAL, bool SMEM_HIST, int kUnroll, int kMinBlocks>
@@ -115,7 +344,6 @@ kid_classify2_kernel(const KidClassifyParams p)
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     WarpStrip &strip = strips[warp_in_block];
-    const unsigned full = 0xFFFFFFFFu;
     const Kid2TableView tab = p.table2;
 
     if (SMEM_HIST) {
@@ -125,276 +353,110 @@ kid_classify2_kernel(const KidClassifyParams p)
     if (lane < kCodeWords - 32) strip.codes[32 + lane] = 0;
     if (lane < kValidWords - 16) { strip.valid[16 + lane] = 0; strip.kmask[16 + lane] = 0; }
 
-    unsigned lane_lookups = 0;        // per lane, reduced once at the end
-    unsigned long long n_hits = 0;    // warp-uniform
+    unsigned long long n_lookups = 0, n_hits = 0; // warp-uniform
 
+    // the read's final taxon: per-read output and gcount[final]++ (:613)
+    auto finish_read = [&](size_t r, int start, int stop, bool kept, uint32_t fin) {
+        if (lane == 0) {
+            if (p.out_span) {
+                p.out_span[2 * r] = (uint32_t)start;
+                p.out_span[2 * r + 1] = (uint32_t)stop;
+            }
+            if (p.out_taxon) p.out_taxon[r] = kept ? (int32_t)fin : -1;
+            if (kept) {
+                if (SMEM_HIST) atomicAdd(&hist[fin], 1);
+                else atomicAdd(&p.gcount[fin], 1);
+            }
+        }
+    };
+
+    const size_t n_groups = (p.n_reads + kGroup - 1) / kGroup;
     const size_t warps_total = (size_t)gridDim.x * kWarpsPerBlock;
-    for (size_t r = (size_t)blockIdx.x * kWarpsPerBlock + warp_in_block; r < p.n_reads;
-         r += warps_total) {
-        const uint64_t g0 = __ldg(p.off + r) - p.off_bias;
-        const int len = (int)(__ldg(p.off + r + 1) - p.off_bias - g0);
-        int start = 0, stop = len - 1;
-
-        // ---- LOAD: bases of window 0 and both quality ends, all independent of each other
+    for (size_t grp = (size_t)blockIdx.x * kWarpsPerBlock + warp_in_block; grp < n_groups; grp += warps_total) {
+        const size_t r0 = grp * kGroup;
+        const int nr = (int)min((size_t)kGroup, p.n_reads - r0);
+        // offsets of the group's reads relative to its first read
+        const uint64_t g0 = __ldg(p.off + r0) - p.off_bias;
+        int rel[kGroup + 1];
+        rel[0] = 0;
+#pragma unroll
+        for (int i = 1; i <= kGroup; i++)
+            rel[i] = i <= nr ? (int)(__ldg(p.off + r0 + i) - p.off_bias - g0) : rel[i - 1];
         const uintptr_t addr0 = reinterpret_cast<uintptr_t>(p.seq) + g0;
         const uintptr_t abase = addr0 & ~(uintptr_t)15;
-        const int delta = (int)(addr0 - abase); // staged index of base 0
-        const int staged_len = delta + len;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (16 * lane < staged_len) v = __ldg(reinterpret_cast<const uint4 *>(abase) + lane);
+        const int delta = (int)(addr0 - abase); // staged index of the group's first base
 
-        // ---- TRIM (:724-753)
-        if (HAS_QUAL && len > 0) {
-            const signed char *q = reinterpret_cast<const signed char *>(p.qual) + g0;
-            const int qa = lane < len ? (int)q[lane] : -128;           // q[0..31]
-            const int qb = lane < len ? (int)q[len - 1 - lane] : -128; // q[len-1 .. len-32]
-            // fast path (most reads): both end bases and both end windows pass -> nothing to trim
-            bool untouched = false;
-            if (len >= 6) {
-                int sa = qa + __shfl_down_sync(full, qa, 1), sb = qb + __shfl_down_sync(full, qb, 1);
-                sa += __shfl_down_sync(full, sa, 2); // lane 0: q[0]+q[1]+q[2]+q[3]
-                sb += __shfl_down_sync(full, sb, 2); // lane 0: q[len-1]+...+q[len-4]
-                untouched = __shfl_sync(full, (int)(qa >= 49 && qb >= 49 && sa - 128 >= 68 && sb - 128 >= 68), 0) != 0;
+        if (delta + rel[kGroup] <= kGroupMaxSpan && rel[kGroup] >= 0) {
+            // ---- grouped path: one load / pack / mask for all reads of the group
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (16 * lane < delta + rel[kGroup]) v = __ldg(reinterpret_cast<const uint4 *>(abase) + lane);
+            if (HAS_QUAL) {
+                const signed char *q = reinterpret_cast<const signed char *>(p.qual) + g0;
+                int qa[kGroup], qb[kGroup];
+#pragma unroll
+                for (int i = 0; i < kGroup; i++) { // all quality loads in flight before any is used
+                    const int len = rel[i + 1] - rel[i];
+                    qa[i] = lane < len ? (int)q[rel[i] + lane] : -128;
+                    qb[i] = lane < len ? (int)q[rel[i + 1] - 1 - lane] : -128;
+                }
+#pragma unroll
+                for (int i = 0; i < kGroup; i++) {
+                    int st, sp;
+                    trim_read(q + rel[i], rel[i + 1] - rel[i], qa[i], qb[i], lane, st, sp);
+                    if (lane == 0) { strip.meta[3 * i] = st; strip.meta[3 * i + 1] = sp; strip.meta[3 * i + 2] = delta + rel[i]; }
+                }
+            } else if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < kGroup; i++) {
+                    strip.meta[3 * i] = 0;
+                    strip.meta[3 * i + 1] = rel[i + 1] - rel[i] - 1;
+                    strip.meta[3 * i + 2] = delta + rel[i];
+                }
             }
-            if (!untouched) {
-            { // while (qual[start] < '1' && start < stop) start++;
-                const unsigned m = __ballot_sync(full, lane < stop && qa >= 49);
-                start = m ? __ffs(m) - 1 : scan_first_good(q, 32, stop, lane);
+            stage_window(strip, v, p.accept_u, lane); // (its __syncwarp()s also publish meta[])
+            for (int i = 0; i < nr; i++) {
+                const int start = strip.meta[3 * i], stop = strip.meta[3 * i + 1], tbase = strip.meta[3 * i + 2];
+                const bool kept = stop - start >= KID_KSIZE; // :755
+                uint32_t fin = 0;
+                if (kept)
+                    scan_kmers<kUnroll>(p, tab, strip, tbase, start, stop - (KID_KSIZE - 1), lane, fin, n_lookups, n_hits);
+                finish_read(r0 + i, start, stop, kept, fin);
             }
-            { // while (qual[stop] < '1' && stop > start) stop--;
-                const unsigned m = __ballot_sync(full, len - 1 - lane > start && qb >= 49);
-                stop = m ? len - 1 - (__ffs(m) - 1) : scan_last_good(q, len - 33, start, lane);
-            }
-            if (start < stop - 4) { // leading 4-base window slides right while sum(q-32) < 68
-                const int lim = stop - 4, s = start + lane;
-                const int w = __shfl_sync(full, qa, s & 31) + __shfl_sync(full, qa, (s + 1) & 31) +
-                              __shfl_sync(full, qa, (s + 2) & 31) + __shfl_sync(full, qa, (s + 3) & 31);
-                const bool known = s + 3 < 32;
-                const unsigned mk = __ballot_sync(full, known && s < lim && w - 128 >= 68);
-                const unsigned unk = __ballot_sync(full, !known && s < lim);
-                if (mk && (!unk || __ffs(mk) < __ffs(unk))) start += __ffs(mk) - 1;
-                else if (!mk && !unk) start = lim;
-                else start = scan_window_fwd(q, start, lim, lane);
-            }
-            if (start < stop - 4) { // trailing window slides left
-                const int lo = start + 4, t = stop - lane;
-                const int idx = len - 1 - t; // lane of qb that holds q[t]
-                const int w = __shfl_sync(full, qb, idx & 31) + __shfl_sync(full, qb, (idx + 1) & 31) +
-                              __shfl_sync(full, qb, (idx + 2) & 31) + __shfl_sync(full, qb, (idx + 3) & 31);
-                const bool known = idx + 3 < 32;
-                const unsigned mk = __ballot_sync(full, known && t > lo && w - 128 >= 68);
-                const unsigned unk = __ballot_sync(full, !known && t > lo);
-                if (mk && (!unk || __ffs(mk) < __ffs(unk))) stop -= __ffs(mk) - 1;
-                else if (!mk && !unk) stop = lo;
-                else stop = scan_window_bwd(q, stop, lo, lane);
-            }
-            } // !untouched
-        }
-        if (p.out_span && lane == 0) {
-            p.out_span[2 * r] = (uint32_t)start;
-            p.out_span[2 * r + 1] = (uint32_t)stop;
-        }
-        if (stop - start < KID_KSIZE) { // :755 - the read vanishes (also covers len <= 30)
-            if (p.out_taxon && lane == 0) p.out_taxon[r] = -1;
+            __syncwarp(); // meta[] is rewritten by the next group
             continue;
         }
 
-        const int last_start = stop - (KID_KSIZE - 1); // last k-mer start position
-        uint32_t fin = 0;
-
-        for (int wb = 0; wb <= last_start; wb += kWindowStarts) {
-            if (wb + kWindowStarts <= start) continue; // window entirely before the trimmed span
-            __syncwarp();
-            if (wb > 0) {
-                v = make_uint4(0, 0, 0, 0);
-                if (wb + 16 * lane < staged_len)
-                    v = __ldg(reinterpret_cast<const uint4 *>(abase + (uintptr_t)wb) + lane);
+        // ---- one read at a time (long reads): windows of kWindowStarts k-mer starts
+        for (int i = 0; i < nr; i++) {
+            const uint64_t gi = g0 + (uint64_t)(int64_t)rel[i];
+            const int len = rel[i + 1] - rel[i];
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.seq) + gi;
+            const uintptr_t ab = a0 & ~(uintptr_t)15;
+            const int dl = (int)(a0 - ab);
+            int start = 0, stop = len - 1;
+            if (HAS_QUAL && len > 0) {
+                const signed char *q = reinterpret_cast<const signed char *>(p.qual) + gi;
+                const int qa = lane < len ? (int)q[lane] : -128;
+                const int qb = lane < len ? (int)q[len - 1 - lane] : -128;
+                trim_read(q, len, qa, qb, lane, start, stop);
             }
-            { // STAGE
-                uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
-                pack4(v.x, p.accept_u, c0, v0);
-                pack4(v.y, p.accept_u, c1, v1);
-                pack4(v.z, p.accept_u, c2, v2);
-                pack4(v.w, p.accept_u, c3, v3);
-                strip.codes[lane] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-                const uint32_t v16 = (v0 << 12) | (v1 << 8) | (v2 << 4) | v3;
-                const uint32_t nb = __shfl_down_sync(full, v16, 1);
-                if ((lane & 1) == 0) strip.valid[lane >> 1] = (v16 << 16) | nb;
-            }
-            __syncwarp();
-
-            // k-mer starts of this window, relative to wb: [first, wcount)
-            const int wcount = min(kWindowStarts, last_start - wb + 1);
-            const int first = max(0, start - wb);
-            { // KMASK: bit (31 - t%32) of word t/32 <=> a valid, in-range k-mer starts at staged index t
-                const int l16 = lane & 15;
-                uint64_t x = ((uint64_t)strip.valid[l16] << 32) | strip.valid[l16 + 1];
-                x &= x << 1; x &= x << 2; x &= x << 4; x &= x << 8; // runs of 16 valid bases
-                x &= x << 14;                                       // runs of 30
-                uint32_t km = (uint32_t)(x >> 32);
-                const int lo_b = delta + first - 32 * l16;          // first allowed bit of this word
-                const int hi_b = delta + wcount - 1 - 32 * l16;     // last allowed bit
-                uint32_t allow = lo_b <= 0 ? 0xFFFFFFFFu : (lo_b >= 32 ? 0u : 0xFFFFFFFFu >> lo_b);
-                if (hi_b < 31) allow &= hi_b < 0 ? 0u : ~(0xFFFFFFFFu >> (hi_b + 1));
-                km &= allow;
-                if (lane < 16) {
-                    strip.kmask[lane] = km;
-                    lane_lookups += __popc(km); // every set bit is exactly one getHash call (:529)
+            const bool kept = stop - start >= KID_KSIZE;
+            uint32_t fin = 0;
+            if (kept) {
+                const int last_start = stop - (KID_KSIZE - 1);
+                for (int wb = 0; wb <= last_start; wb += kWindowStarts) {
+                    if (wb + kWindowStarts <= start) continue; // window entirely before the trimmed span
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (wb + 16 * lane < dl + len) v = __ldg(reinterpret_cast<const uint4 *>(ab + (uintptr_t)wb) + lane);
+                    stage_window(strip, v, p.accept_u, lane);
+                    scan_kmers<kUnroll>(p, tab, strip, dl, max(0, start - wb), min(kWindowStarts - 1, last_start - wb),
+                                        lane, fin, n_lookups, n_hits);
                 }
             }
-            __syncwarp();
-
-            auto block128 = [&](int c, auto full_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                // chunks (of 32 k-mers) this iteration has; FULL == all four, known at compile time
-                const int nch = FULL ? kUnroll : min(kUnroll, (wcount - c + 31) >> 5);
-                uint32_t cm[kUnroll + 1]; // 16-mer hashes -> sliding minima
-                uint64_t key[kUnroll];
-                // KEYS
-#pragma unroll
-                for (int u = 0; u <= kUnroll; u++) {
-                    cm[u] = 0xFFFFFFFFu;
-                    if (FULL || u <= nch) { // chunk nch is the 14-lane halo of chunk nch-1
-                        const int t = delta + c + 32 * u + lane; // staged index of this lane's base
-                        const int w = t >> 4, sh = (t & 15) * 2;
-                        const uint32_t w0 = strip.codes[w], w1 = strip.codes[w + 1];
-                        const uint32_t hi = __funnelshift_l(w1, w0, sh);
-                        const uint32_t rc = kid_rc16(hi);
-                        cm[u] = kid_mm_hash_canon(min(hi, rc));
-                        if (u < kUnroll) {
-                            // forward key = first 30 of the 32 bases at this position; the reverse
-                            // complement of 32 bases is rc16(low half) : rc16(high half) and its low
-                            // 60 bits are the reverse complement of the first 30 bases
-                            const uint32_t lo = __funnelshift_l(strip.codes[w + 2], w1, sh);
-                            const uint64_t kf = (((uint64_t)hi << 32) | lo) >> 4;
-                            const uint64_t kr = (((uint64_t)kid_rc16(lo) << 32) | rc) & KID_MASK60;
-                            key[u] = kf < kr ? kf : kr; // :528
-                        }
-                    }
-                }
-                // MINIM: window minimum over 15 consecutive positions (1 + 2 + 4 + 7 doubling)
-#pragma unroll
-                for (int step = 0; step < 4; step++) {
-                    const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
-                    const int src = lane + d; // shfl takes the source lane modulo 32
-                    const bool wrap = lane + d >= 32;
-                    uint32_t s[kUnroll + 1];
-#pragma unroll
-                    for (int u = 0; u <= kUnroll; u++)
-                        if (FULL || u <= nch) s[u] = __shfl_sync(full, cm[u], src);
-#pragma unroll
-                    for (int u = 0; u < kUnroll; u++)
-                        if (FULL || u < nch) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
-                    if (FULL) cm[kUnroll] = min(cm[kUnroll], wrap ? 0xFFFFFFFFu : s[kUnroll]);
-                    else {
-#pragma unroll
-                        for (int u = 1; u < kUnroll; u++)
-                            if (u == nch) cm[u] = min(cm[u], wrap ? 0xFFFFFFFFu : s[u]);
-                    }
-                }
-                // LOOKUP: issue every sector load before consuming any.  Inactive lanes (k-mer with an
-                // N, or past the read) read sector 0 instead of branching; their result is ignored.
-                uint4 ea[kUnroll], eb[kUnroll];
-                uint32_t sec[kUnroll]; // sector index (< 2^32: at most 2^30 lines)
-                bool act[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; u++) {
-                    act[u] = false;
-                    if (FULL || u < nch) {
-                        const int t = delta + c + 32 * u + lane;
-                        act[u] = (int32_t)(strip.kmask[t >> 5] << (t & 31)) < 0;
-                        const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
-                        sec[u] = (line << 2) | kid_key_sector(key[u]);
-                        kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
-                    }
-                }
-                // MATCH round 1: just "hit" and "sector full without a match" per lane
-                bool hit[kUnroll];
-                uint32_t again = 0;
-#pragma unroll
-                for (int u = 0; u < kUnroll; u++) {
-                    hit[u] = false;
-                    if (FULL || u < nch) {
-                        const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                        const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
-                                       (eb[u].x == klo && eb[u].y == khi);
-                        hit[u] = act[u] && h;
-                        // all three entries carry bit 63 and none matched: the key may live further on
-                        const bool more = act[u] && !h && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
-                        again |= more ? (1u << u) : 0u;
-                    }
-                }
-                // MATCH round 2 for the few lanes that met a full sector: all loads first
-                if (__any_sync(full, again != 0)) {
-#pragma unroll
-                    for (int u = 0; u < kUnroll; u++)
-                        if (FULL || u < nch)
-                            kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
-#pragma unroll
-                    for (int u = 0; u < kUnroll; u++) {
-                        if ((FULL || u < nch) && ((again >> u) & 1u)) {
-                            const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                            uint32_t tx = 0;
-                            int j = 0;
-                            const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
-                            if (res > 0) {
-                                hit[u] = true;
-                                sec[u] = sec[u] + 1; // slack sectors follow the last home sector
-                            } else if (res < 0) { // rare: third sector and on
-                                uint64_t slot = 0;
-                                if (kid2_lookup_from(tab, sec[u], key[u], 2, slot)) {
-                                    hit[u] = true;
-                                    sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
-                                    kid2_load_sector(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u]);
-                                }
-                            }
-                        }
-                    }
-                }
-                // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
-#pragma unroll
-                for (int u = 0; u < kUnroll; u++) {
-                    if (!FULL && u >= nch) break; // warp-uniform
-                    unsigned m = __ballot_sync(full, hit[u]);
-                    if (m) {
-                        uint32_t taxon = 0;
-                        if (hit[u]) {
-                            const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                            int j = 0;
-                            kid2_match(ea[u], eb[u], klo, khi, taxon, j);
-                            if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
-                                const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
-                                atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
-                            }
-                        }
-                        n_hits += __popc(m);
-                        do { // ordered left fold over the hits of this chunk (:588-595)
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const uint32_t tj = __shfl_sync(full, taxon, src);
-                            if (fin > 0) { if (tj != fin) fin = kid_msca(p.tree, tj, fin); }
-                            else fin = tj;
-                        } while (m);
-                    }
-                }
-            };
-
-            for (int c = (first / 32) * 32; c < wcount; c += 32 * kUnroll) {
-                if (wcount - c > 32 * (kUnroll - 1)) block128(c, std::true_type{});
-                else block128(c, std::false_type{});
-            }
-        }
-
-        // ---- COUNT (:613)
-        if (lane == 0) {
-            if (p.out_taxon) p.out_taxon[r] = (int32_t)fin;
-            if (SMEM_HIST) atomicAdd(&hist[fin], 1);
-            else atomicAdd(&p.gcount[fin], 1);
+            finish_read(r0 + i, start, stop, kept, fin);
         }
     }
 
-    unsigned long long n_lookups = lane_lookups;
-    for (int o = 16; o; o >>= 1) n_lookups += __shfl_xor_sync(full, n_lookups, o);
     if (lane == 0) {
         if (n_lookups) atomicAdd(p.counters + 0, n_lookups);
         if (n_hits) atomicAdd(p.counters + 1, n_hits);
@@ -423,7 +485,7 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     size_t blocks = (size_t)sm_count * per_sm; // persistent: a whole number of resident waves
-    const size_t need = (p.n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t need = ((p.n_reads + kGroup - 1) / kGroup + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > need) blocks = need;
     if (blocks == 0) return cudaSuccess;
     kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
