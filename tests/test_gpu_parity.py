@@ -254,3 +254,47 @@ def test_msca_deep_tree():
     batch = H.make_reads(rng, db, 1500)
     _check_batch(gs, osamp, batch)
     _check_counts(gs, osamp)
+
+
+def test_sample_end_kernels_with_two_shards_on_one_gpu(layout):
+    """The multi-GPU sample-end kernels, exercised on ONE device: two samples play two ranks (same
+    replica, different shards, 300 reads in common).  Both transports - OR into a slice then
+    histogram (kid_seen_or_device + kid_ucount_range_device) and the fused peer kernel
+    (kid_ucount_or_range_device) - must give the ucount of the union, which is NOT the sum."""
+    import torch
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(71)
+    db = H.make_db(rng, 20000)
+    odb, osamp = _oracle(db)
+    gdb, s0 = _gpu(db, layout)
+    s1 = kid.Sample(gdb)
+    common = H.make_reads(rng, db, 300, name_prefix="C")
+    shards = [H.make_reads(rng, db, 1500, name_prefix="A"), H.make_reads(rng, db, 1500, name_prefix="B")]
+    per_shard_u = []
+    for s, sh in zip((s0, s1), shards):
+        for b in (sh, common):
+            seq, qual = b.padded()
+            s.classify(seq, qual, b.off)
+            osamp.classify(b.seq, b.qual, b.off)
+        per_shard_u.append(s.counts()[1])
+    want_u = osamp.ucount
+    assert not np.array_equal(per_shard_u[0] + per_shard_u[1], want_u), "fixture must make the naive sum wrong"
+    p0, n_words = s0.seen_device()
+    p1, _ = s1.seen_device()
+    dev = torch.device("cuda:0")
+    half = n_words // 2
+    assert half % 4 == 0
+    # fused: each "rank" histograms its half of the OR of both bitmaps, partials add up
+    part = [torch.zeros(gdb.n_taxa, dtype=torch.int32, device=dev) for _ in range(2)]
+    s0.ucount_or_range([p0, p1], 0, half, part[0])
+    s1.ucount_or_range([p0, p1], half, n_words - half, part[1])
+    torch.cuda.synchronize()
+    assert np.array_equal((part[0] + part[1]).cpu().numpy(), want_u)
+    # staged: OR both bitmaps' slice into a scratch buffer placed at the slice's own position
+    scratch = torch.zeros(n_words, dtype=torch.int32, device=dev)
+    part2 = torch.zeros(gdb.n_taxa, dtype=torch.int32, device=dev)
+    for w0, n in ((0, half), (half, n_words - half)):
+        s0.seen_or(scratch.data_ptr() + 4 * w0, [p0, p1], w0, n)
+        s0.ucount_range(scratch.data_ptr(), w0, n, part2)
+    torch.cuda.synchronize()
+    assert np.array_equal(part2.cpu().numpy(), want_u)
