@@ -124,6 +124,10 @@ int kid_sample_transfer_bytes(const kid_sample *s, uint64_t *h2d, uint64_t *d2h)
  * per-taxon histogram of seen flags (equivalent to :596-603) and copies
  * gcount/ucount (int32[n_taxa]) to the host.  Synchronous.  Either pointer may be NULL. */
 int kid_sample_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *stream);
+/* Same for ONE sample whose reads were split over n kid_sample objects of the same kid_db on the
+ * same device (e.g. R1 and R2 classified concurrently by two host threads): gcount is summed,
+ * ucount is the histogram of the OR of their seen flags (a k-mer hit in both shards counts once). */
+int kid_samples_counts(kid_sample *const *samples, int n, int32_t *gcount, int32_t *ucount, void *stream);
 /* number of getHash calls (:529), hits (target > 0) and reads counted in gcount ("tct", :614) */
 int kid_sample_counters(kid_sample *s, uint64_t *lookups, uint64_t *hits, uint64_t *reads,
                         void *stream);

@@ -55,6 +55,7 @@ _SIGS = {
     "kid_sample_set_chunk_reads": (_i, [_vp, _sz]),
     "kid_sample_transfer_bytes": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "kid_sample_counts": (_i, [_vp, _vp, _vp, _vp]),
+    "kid_samples_counts": (_i, [C.POINTER(_vp), _i, _vp, _vp, _vp]),
     "kid_sample_counters": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "kid_sample_gcount_device": (_i, [_vp, C.POINTER(_vp)]),
     "kid_sample_seen_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),

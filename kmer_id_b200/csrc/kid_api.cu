@@ -571,6 +571,37 @@ int kid_sample_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *str
     return KID_OK;
 }
 
+int kid_samples_counts(kid_sample *const *samples, int n, int32_t *gcount, int32_t *ucount, void *stream_)
+{
+    if (!samples || n < 1 || n > KID_MAX_OR_SOURCES) return fail(KID_EINVAL, "kid_samples_counts: bad argument");
+    for (int i = 0; i < n; i++)
+        if (!samples[i] || samples[i]->db != samples[0]->db)
+            return fail(KID_EINVAL, "kid_samples_counts: samples must share one kid_db");
+    kid_sample *s0 = samples[0];
+    DeviceGuard guard(s0->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t nt = (size_t)s0->db->n_taxa, nb = sizeof(int) * nt;
+    if (ucount) {
+        KidPtrList l;
+        for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i < n ? samples[i]->seen : nullptr;
+        KID_CUDA(cudaMemsetAsync(s0->ucount, 0, nb, stream));
+        KID_CUDA(kid_launch_ucount_or(s0->db->table_ptr(), s0->db->layout, l, n, 0, s0->n_words, s0->ucount,
+                                      s0->db->n_taxa, stream));
+        KID_CUDA(cudaMemcpyAsync(ucount, s0->ucount, nb, cudaMemcpyDeviceToHost, stream));
+    }
+    if (gcount) {
+        std::vector<int32_t> tmp(nt);
+        memset(gcount, 0, nb);
+        for (int i = 0; i < n; i++) {
+            KID_CUDA(cudaMemcpyAsync(tmp.data(), samples[i]->gcount, nb, cudaMemcpyDeviceToHost, stream));
+            KID_CUDA(cudaStreamSynchronize(stream));
+            for (size_t t = 0; t < nt; t++) gcount[t] += tmp[t];
+        }
+    }
+    KID_CUDA(cudaStreamSynchronize(stream));
+    return KID_OK;
+}
+
 int kid_sample_counters(kid_sample *s, uint64_t *lookups, uint64_t *hits, uint64_t *reads, void *stream_)
 {
     if (!s) return fail(KID_EINVAL, "kid_sample_counters: s is NULL");

@@ -21,6 +21,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace kidhost;
@@ -50,8 +51,17 @@ struct SampleState {
     long long tct = 0;
 };
 
-// classify one FASTQ file batch by batch; appends to _reads.txt exactly as process_read :608-614
-void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream &outread)
+struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is complete
+    int taxon;
+    std::string text; // ">taxon:acc\nbases\n"
+};
+
+// Classify one FASTQ file batch by batch.  direct = R1: append to _reads.txt exactly as process_read
+// :608-614 does.  Otherwise (R2, running concurrently with R1) keep the first SAVENUM records per
+// taxon in stream order; main() writes those that the reference would have written once R1's
+// per-taxon counts are known.
+void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream *outread,
+              std::vector<SavedRead> *saved)
 {
     ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 19, (size_t)96 << 20);
     std::vector<int32_t> taxon;
@@ -67,11 +77,23 @@ void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::of
                 const int fin = taxon[r];
                 if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
                 if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) {
-                    outread << ">" << fin << ":";
-                    outread.write(b->names.data() + b->name_off[r], b->name_off[r + 1] - b->name_off[r]);
-                    outread << std::endl;
-                    outread.write((const char *)b->seq + b->off[r] + span[2 * r], span[2 * r + 1] - span[2 * r] + 1);
-                    outread << std::endl;
+                    const char *name = b->names.data() + b->name_off[r];
+                    const size_t nlen = b->name_off[r + 1] - b->name_off[r];
+                    const char *bases = (const char *)b->seq + b->off[r] + span[2 * r];
+                    const size_t blen = span[2 * r + 1] - span[2 * r] + 1;
+                    if (outread) {
+                        *outread << ">" << fin << ":";
+                        outread->write(name, (std::streamsize)nlen);
+                        *outread << std::endl;
+                        outread->write(bases, (std::streamsize)blen);
+                        *outread << std::endl;
+                    } else {
+                        SavedRead sr;
+                        sr.taxon = fin;
+                        sr.text = ">" + std::to_string(fin) + ":" + std::string(name, nlen) + "\n" +
+                                  std::string(bases, blen) + "\n";
+                        saved->push_back(std::move(sr));
+                    }
                 }
                 st.gcount_host[(size_t)fin]++;
                 st.tct++;
@@ -133,29 +155,62 @@ int main(int argc, char *argv[])
         return EXIT_FAILURE;
     }
 
-    kid_sample *smp = nullptr;
+    // R1 and R2 are inflated, parsed and classified concurrently, each into its own kid_sample
+    // (gcount and the seen flags are order independent); the library merges the two at sample end.
+    // KID_SERIAL=1 processes R1 then R2 on one sample, like the reference.
+    const bool serial = getenv("KID_SERIAL") != nullptr;
+    kid_sample *smp = nullptr, *smp2 = nullptr;
     if (kid_sample_create(db, &smp) != 0) die(1, kid_last_error());
+    if (!serial && kid_sample_create(db, &smp2) != 0) die(1, kid_last_error());
     std::vector<int32_t> gcount((size_t)MAXTAR), ucount((size_t)MAXTAR);
     for (const std::string &s : fnames) {
         const double ts = now();
         if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error()); // :1017-1019
-        SampleState st;
+        if (smp2 && kid_sample_begin(smp2, nullptr) != 0) die(1, kid_last_error());
+        SampleState st, st2;
         st.gcount_host.assign((size_t)MAXTAR, 0);
+        st2.gcount_host.assign((size_t)MAXTAR, 0);
         const std::string oname2 = dname + s + "_result.txt", trname = dname + s + "_reads.txt";
         std::cout << s << std::endl; // :1022
         std::ofstream outread(trname.c_str(), std::ofstream::out | std::ofstream::trunc);
-        run_file(smp, dname + s + e1, st, outread);
-        std::cout << st.tct << " reads loaded" << std::endl; // :1030
-        run_file(smp, dname + s + e2, st, outread);
-        std::cout << st.tct << " reads loaded" << std::endl; // :1036
+        long long tct_total = 0;
+        if (serial) {
+            run_file(smp, dname + s + e1, st, &outread, nullptr);
+            std::cout << st.tct << " reads loaded" << std::endl; // :1030
+            run_file(smp, dname + s + e2, st, &outread, nullptr);
+            tct_total = st.tct;
+            if (kid_sample_counts(smp, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
+        } else {
+            std::vector<SavedRead> saved;
+            std::thread t2([&] { run_file(smp2, dname + s + e2, st2, nullptr, &saved); });
+            run_file(smp, dname + s + e1, st, &outread, nullptr);
+            std::cout << st.tct << " reads loaded" << std::endl; // :1030
+            t2.join();
+            // an R2 read is written iff fewer than SAVENUM reads of its taxon came before it, R1 first
+            std::vector<int> seen_r2((size_t)MAXTAR, 0);
+            for (const SavedRead &sr : saved) {
+                if (st.gcount_host[(size_t)sr.taxon] + seen_r2[(size_t)sr.taxon] < SAVENUM) outread << sr.text << std::flush;
+                seen_r2[(size_t)sr.taxon]++;
+            }
+            tct_total = st.tct + st2.tct;
+            kid_sample *both[2] = { smp, smp2 };
+            if (kid_samples_counts(both, 2, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
+        }
+        std::cout << tct_total << " reads loaded" << std::endl; // :1036
         outread.close();
-        if (kid_sample_counts(smp, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
         std::ofstream out2(oname2);
         for (int i = 0; i < MAXTAR; i++) out2 << i << "," << gcount[(size_t)i] << "," << ucount[(size_t)i] << "\n";
         out2.close();
+        st.tct = tct_total;
         if (stats) {
             uint64_t lk = 0, hits = 0, rd = 0;
             kid_sample_counters(smp, &lk, &hits, &rd, nullptr);
+            if (smp2) {
+                uint64_t lk2 = 0, hits2 = 0;
+                kid_sample_counters(smp2, &lk2, &hits2, &rd, nullptr);
+                lk += lk2;
+                hits += hits2;
+            }
             fprintf(stderr, "[nk10] %s: %lld reads, %llu lookups, %llu hits in %.3f s\n", s.c_str(), st.tct,
                     (unsigned long long)lk, (unsigned long long)hits, now() - ts);
         }
@@ -165,6 +220,7 @@ int main(int argc, char *argv[])
                 t2 - t1, now() - t0);
     (void)cached;
     kid_sample_free(smp);
+    kid_sample_free(smp2);
     kid_db_free(db);
     return 0;
 }

@@ -26,13 +26,18 @@ def _run_both(work, fq):
             p = os.path.join(fq, f)
             ref_files[f] = open(p, "rb").read()
             os.remove(p)
-    r_gpu = H.run_nk10(NK_GPU, work, fq)
-    assert r_gpu.returncode == 0, r_gpu.stderr.decode()
-    assert r_gpu.stdout == r_ref.stdout
-    assert ref_files
-    for f, want in ref_files.items():
-        got = open(os.path.join(fq, f), "rb").read()
-        assert got == want, f"{f} differs from the reference's"
+    # default = R1 and R2 classified concurrently on two samples; KID_SERIAL=1 = one after the other
+    for env in ({}, {"KID_SERIAL": "1"}):
+        r_gpu = subprocess.run([NK_GPU, fq if fq.endswith("/") else fq + "/"], cwd=work, capture_output=True,
+                               timeout=600, env=dict(os.environ, **env))
+        assert r_gpu.returncode == 0, r_gpu.stderr.decode()
+        assert r_gpu.stdout == r_ref.stdout
+        assert ref_files
+        for f, want in ref_files.items():
+            p = os.path.join(fq, f)
+            got = open(p, "rb").read()
+            os.remove(p)
+            assert got == want, f"{f} differs from the reference's ({env})"
     return ref_files
 
 
@@ -48,6 +53,7 @@ def test_config0_synthetic_100k_pairs(tmp_path):
     files = _run_both(work, fq)
     res = files["cfg0_result.txt"].decode().split("\n")
     assert len(res) == H.B10_NTAXA + 1
+    open(os.path.join(fq, "cfg0_result.txt"), "wb").write(files["cfg0_result.txt"])
     g_, u_ = H.read_result(os.path.join(fq, "cfg0_result.txt"))
     assert g_.sum() == 200000 and g_[0] < 80000 and u_.sum() > 100000
 
