@@ -187,7 +187,7 @@ __device__ __forceinline__ void stage_window(WarpStrip &strip, const uint4 &v, b
 template <int kUnroll>
 __device__ __forceinline__ void scan_kmers(const KidClassifyParams &p, const Kid2TableView &tab, const WarpStrip &strip,
                                            int tbase, int first, int last, int lane, uint32_t &fin,
-                                           unsigned long long &n_lookups, unsigned long long &n_hits)
+                                           unsigned &lane_lookups, unsigned long long &n_hits)
 {
     const unsigned full = 0xFFFFFFFFu;
     auto blockN = [&](int c, auto full_tag) {
@@ -249,7 +249,7 @@ __device__ __forceinline__ void scan_kmers(const KidClassifyParams &p, const Kid
             if (FULL || u < nch) {
                 const int j = c + 32 * u + lane, t = tbase + j;
                 act[u] = (int32_t)(strip.kmask[t >> 5] << (t & 31)) < 0 && j >= first && j <= last;
-                n_lookups += __popc(__ballot_sync(full, act[u])); // each is one getHash call (:529)
+                lane_lookups += act[u]; // each is one getHash call (:529); summed over lanes at the end
                 const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
                 sec[u] = (line << 2) | kid_key_sector(key[u]);
                 kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
@@ -353,7 +353,8 @@ kid_classify2_kernel(const KidClassifyParams p)
     if (lane < kCodeWords - 32) strip.codes[32 + lane] = 0;
     if (lane < kValidWords - 16) { strip.valid[16 + lane] = 0; strip.kmask[16 + lane] = 0; }
 
-    unsigned long long n_lookups = 0, n_hits = 0; // warp-uniform
+    unsigned lane_lookups = 0;     // per lane (< 2^32 per launch), reduced once at the end
+    unsigned long long n_hits = 0; // warp-uniform
 
     // the read's final taxon: per-read output and gcount[final]++ (:613)
     auto finish_read = [&](size_t r, int start, int stop, bool kept, uint32_t fin) {
@@ -419,7 +420,7 @@ kid_classify2_kernel(const KidClassifyParams p)
                 const bool kept = stop - start >= KID_KSIZE; // :755
                 uint32_t fin = 0;
                 if (kept)
-                    scan_kmers<kUnroll>(p, tab, strip, tbase, start, stop - (KID_KSIZE - 1), lane, fin, n_lookups, n_hits);
+                    scan_kmers<kUnroll>(p, tab, strip, tbase, start, stop - (KID_KSIZE - 1), lane, fin, lane_lookups, n_hits);
                 finish_read(r0 + i, start, stop, kept, fin);
             }
             __syncwarp(); // meta[] is rewritten by the next group
@@ -450,13 +451,15 @@ kid_classify2_kernel(const KidClassifyParams p)
                     if (wb + 16 * lane < dl + len) v = __ldg(reinterpret_cast<const uint4 *>(ab + (uintptr_t)wb) + lane);
                     stage_window(strip, v, p.accept_u, lane);
                     scan_kmers<kUnroll>(p, tab, strip, dl, max(0, start - wb), min(kWindowStarts - 1, last_start - wb),
-                                        lane, fin, n_lookups, n_hits);
+                                        lane, fin, lane_lookups, n_hits);
                 }
             }
             finish_read(r0 + i, start, stop, kept, fin);
         }
     }
 
+    unsigned long long n_lookups = lane_lookups;
+    for (int o = 16; o; o >>= 1) n_lookups += __shfl_xor_sync(0xFFFFFFFFu, n_lookups, o);
     if (lane == 0) {
         if (n_lookups) atomicAdd(p.counters + 0, n_lookups);
         if (n_hits) atomicAdd(p.counters + 1, n_hits);
