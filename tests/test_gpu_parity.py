@@ -298,3 +298,44 @@ def test_sample_end_kernels_with_two_shards_on_one_gpu(layout):
         s0.ucount_range(scratch.data_ptr(), w0, n, part2)
     torch.cuda.synchronize()
     assert np.array_equal(part2.cpu().numpy(), want_u)
+
+
+def test_trim_adversarial_qualities(layout):
+    """process_qual (:714-760) corner cases: every length 1..70 and longer ones, quality strings made
+    of runs around the two thresholds (single base >= '1', 4-window sum(q-32) >= 68), good/bad
+    islands near both ends, bytes >= 0x80 (negative as signed char).  Spans and drop decisions must
+    match the oracle bit for bit - this exercises the fast path, the preloaded-register path and the
+    32-positions-per-step fallback scans of the CUDA trim."""
+    rng = np.random.default_rng(81)
+    db = H.make_db(rng, 2000)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db, layout)
+    alphabet = np.array([33, 35, 47, 48, 49, 50, 51, 52, 53, 60, 73, 127, 128, 200, 255], dtype=np.uint8)
+    seqs, quals = [], []
+    lengths = list(range(1, 71)) * 40 + list(rng.integers(71, 400, size=3000)) + [511, 512, 513, 1000] * 10
+    for L in lengths:
+        L = int(L)
+        mode = rng.integers(0, 5)
+        if mode == 0:
+            q = rng.choice(alphabet, size=L)
+        elif mode == 1:  # runs
+            q = np.repeat(rng.choice(alphabet, size=L), rng.integers(1, 9, size=L))[:L]
+        elif mode == 2:  # good middle, ragged ends
+            q = np.full(L, 73, np.uint8)
+            a, b = int(rng.integers(0, min(L, 45))), int(rng.integers(0, min(L, 45)))
+            q[:a] = rng.choice(alphabet[:9], size=a)
+            q[L - b:] = rng.choice(alphabet[:9], size=b)
+        elif mode == 3:  # borderline windows: values 48..52 only
+            q = rng.integers(48, 53, size=L).astype(np.uint8)
+        else:  # mostly bad with a few good islands
+            q = np.full(L, 35, np.uint8)
+            for _ in range(int(rng.integers(0, 4))):
+                a = int(rng.integers(0, L))
+                q[a:a + int(rng.integers(1, 40))] = 73
+        seqs.append(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=L)])
+        quals.append(q[:L])
+    off = np.concatenate([[0], np.cumsum([s.size for s in seqs])]).astype(np.uint64)
+    batch = H.ReadBatch(seq=np.concatenate(seqs), qual=np.concatenate(quals), off=off, names=[])
+    fin = _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
+    assert (fin == -1).sum() > 1000 and (fin >= 0).sum() > 1000
