@@ -378,16 +378,18 @@ kid_classify2_kernel(const KidClassifyParams p)
         const int nr = (int)min((size_t)kGroup, p.n_reads - r0);
         // offsets of the group's reads relative to its first read
         const uint64_t g0 = __ldg(p.off + r0) - p.off_bias;
-        int rel[kGroup + 1];
+        int rel[kGroup + 1]; // saturated: anything beyond the window size only has to fail the test below
         rel[0] = 0;
 #pragma unroll
-        for (int i = 1; i <= kGroup; i++)
-            rel[i] = i <= nr ? (int)(__ldg(p.off + r0 + i) - p.off_bias - g0) : rel[i - 1];
+        for (int i = 1; i <= kGroup; i++) {
+            const uint64_t d = i <= nr ? __ldg(p.off + r0 + i) - p.off_bias - g0 : (uint64_t)rel[i - 1];
+            rel[i] = d > 0x7FFFFFFFull ? 0x7FFFFFFF : (int)d;
+        }
         const uintptr_t addr0 = reinterpret_cast<uintptr_t>(p.seq) + g0;
         const uintptr_t abase = addr0 & ~(uintptr_t)15;
         const int delta = (int)(addr0 - abase); // staged index of the group's first base
 
-        if (delta + rel[kGroup] <= kGroupMaxSpan && rel[kGroup] >= 0) {
+        if (rel[kGroup] <= kGroupMaxSpan - delta) {
             // ---- grouped path: one load / pack / mask for all reads of the group
             uint4 v = make_uint4(0, 0, 0, 0);
             if (16 * lane < delta + rel[kGroup]) v = __ldg(reinterpret_cast<const uint4 *>(abase) + lane);
@@ -429,8 +431,8 @@ kid_classify2_kernel(const KidClassifyParams p)
 
         // ---- one read at a time (long reads): windows of kWindowStarts k-mer starts
         for (int i = 0; i < nr; i++) {
-            const uint64_t gi = g0 + (uint64_t)(int64_t)rel[i];
-            const int len = rel[i + 1] - rel[i];
+            const uint64_t gi = __ldg(p.off + r0 + i) - p.off_bias; // exact 64-bit offsets (one read < 2^31 bases)
+            const int len = (int)(__ldg(p.off + r0 + i + 1) - p.off_bias - gi);
             const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.seq) + gi;
             const uintptr_t ab = a0 & ~(uintptr_t)15;
             const int dl = (int)(a0 - ab);
