@@ -1,0 +1,67 @@
+// host_dump - TEST INFRASTRUCTURE: drives the C++ host parsers of kmer_id_b200/host without a GPU so
+// that `pytest -m "not gpu"` can check them (the product hosts link the CUDA library instead of the
+// three malloc-backed stubs below).
+//   host_dump probes <probes.gz> <signed 0|1> <cap_log2_cells or 0>   -> "lines N\n" then "key taxon" per entry
+//   host_dump reads  <gzfastq|fastq|gzfasta|fasta> <file>             -> one record per line: acc \t seq \t qual
+//   host_dump tree   <tree file> <n_taxa>                             -> parent[] one per line, or "ERR msg"
+#include "../../include/kmer_id.h"
+#include "../../kmer_id_b200/host/db_loader.hpp"
+#include "../../kmer_id_b200/host/read_reader.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+extern "C" {
+int kid_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -3; }
+void kid_host_free(void *p) { free(p); }
+const char *kid_last_error(void) { return "host_dump stub"; }
+}
+
+using namespace kidhost;
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) return 2;
+    const std::string cmd = argv[1];
+    if (cmd == "probes") {
+        ProbeSet ps;
+        load_probes_gz(argv[2], ps, argc > 3 && atoi(argv[3]) != 0, 3);
+        size_t hidden = 0;
+        if (argc > 4 && atoi(argv[4]) > 0) hidden = apply_reference_probe_cap(ps, 16, atoi(argv[4]));
+        printf("lines %lld hidden %zu\n", ps.lines_parsed, hidden);
+        for (size_t i = 0; i < ps.keys.size(); i++) printf("%llu %u\n", (unsigned long long)ps.keys[i], ps.taxa[i]);
+        return 0;
+    }
+    if (cmd == "reads") {
+        const std::string k = argv[2];
+        const ReadFormat fmt = k == "gzfastq" ? ReadFormat::GzFastq : k == "fastq" ? ReadFormat::PlainFastq
+                             : k == "gzfasta" ? ReadFormat::GzFasta : ReadFormat::PlainFasta;
+        ReadBatchReader reader(fmt, argv[3], 7, 4096, 2); // tiny batches: exercise the batch boundaries
+        for (;;) {
+            ReadBatch *b = reader.next();
+            for (size_t r = 0; r < b->n; r++) {
+                fwrite(b->names.data() + b->name_off[r], 1, b->name_off[r + 1] - b->name_off[r], stdout);
+                fputc('\t', stdout);
+                fwrite(b->seq + b->off[r], 1, b->off[r + 1] - b->off[r], stdout);
+                fputc('\t', stdout);
+                if (b->has_qual) fwrite(b->qual + b->off[r], 1, b->off[r + 1] - b->off[r], stdout);
+                fputc('\n', stdout);
+            }
+            const bool last = b->last;
+            reader.recycle(b);
+            if (last) break;
+        }
+        if (reader.open_failed()) printf("OPEN_FAILED\n");
+        return 0;
+    }
+    if (cmd == "tree") {
+        std::vector<int32_t> parent;
+        std::string msg;
+        if (!load_tree(argv[2], atoi(argv[3]), parent, msg)) { printf("ERR %s\n", msg.c_str()); return 0; }
+        for (int32_t p : parent) printf("%d\n", p);
+        return 0;
+    }
+    return 2;
+}
