@@ -132,6 +132,39 @@ def traffic_per_lookup():
     return None
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this rank (and therefore its first-touch pinned host buffers) to the NUMA node its GPU hangs
+    off, so that with N ranks the H2D streams do not all cross the inter-socket link.  Plumbing only;
+    silently does nothing when sysfs does not say."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id
+    except Exception:
+        bdf = None
+    try:
+        if not bdf:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 # ------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import numpy as np
@@ -149,6 +182,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
@@ -293,6 +327,7 @@ def run_ours(args):
         "sample_end": {"peer": "one fused OR+histogram kernel over NVLink-mapped peer bitmaps + 2 small all-reduces",
                        "nccl": "all-to-all of bitmap slices + OR kernel + histogram kernel + 2 small all-reduces"}[transport]
                       if world > 1 else "single GPU: histogram kernel",
+        "numa_node_rank0": numa,
         "hit_fraction": counters["hits"] / max(1, lookups),
         "classified_fraction": float((gcount[2:].sum()) / max(1, gcount.sum())),
     }
