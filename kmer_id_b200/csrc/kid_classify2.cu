@@ -3,8 +3,8 @@
 // Replaces, for a whole batch of reads, process_qual (newkmer_10nx.cpp:714-760), process_read
 // (:452-617), Hashtable::getHash (:204-233) and Tree1::msca (:118-144).
 //
-// One warp owns one read at a time (persistent grid, warp-strided reads); lane j of chunk c owns
-// the k-mer that starts at base 32c+j.
+// Persistent grid; a warp works on one read at a time and lane j of chunk c owns the k-mer that
+// starts at base 32c+j of that read.
 //   GROUP   a warp takes kGroup (3) consecutive reads at a time; when they fit one 512-base window
 //           (always for 150-bp reads) they are loaded, packed and masked ONCE, which cuts the
 //           per-read prologue by ~2/3.  Longer reads take the one-read-at-a-time path (windows of

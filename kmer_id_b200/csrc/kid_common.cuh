@@ -13,10 +13,12 @@
 //   entry   = rem << 26 | disp << 22 | taxon      one uint64; 0 = empty (taxon 0 is never stored)
 //   bucket  = 4 entries = 32 bytes, 32-byte aligned  -> one sector, one LDG.256
 //
-// A key that does not fit its home bucket goes to bucket home+disp (disp <= 15, stored so that the
-// remainder still identifies the key).  Buckets only ever fill up, so a lookup may stop at the
-// first bucket that has an empty slot.  At the default load (<= 1 key per bucket on average) a
-// second sector is needed by ~1 % of lookups.
+// A key that does not fit its home bucket lives in bucket home+disp (disp <= 15, stored so that the
+// remainder still identifies the key; placement by kid_build_sorted.cu, slack buckets instead of
+// wrap-around).  Every slot between a key's home and its slot is occupied, so a lookup may stop at
+// the first bucket that has an empty slot.  At the default load (<= 1 key per bucket on average)
+// a second sector is needed by ~1 % of lookups.  This is "layout K", kept for the bake-off against
+// the minimizer-addressed layout M (kid_table2.cuh), which is the default.
 //
 // "seen" flags (the reference's std::set kmer_seen, :64,:596-603) are one bit per slot in a
 // separate per-sample bitmap, so the table itself is read-only on the hot path.
@@ -26,10 +28,9 @@
 
 #define KID_TAXON_BITS 22
 #define KID_DISP_BITS 4
-#define KID_TAG_SHIFT (KID_TAXON_BITS + KID_DISP_BITS) /* 26 */
 #define KID_TAXON_MASK ((1u << KID_TAXON_BITS) - 1u)
 #define KID_MAX_DISP ((1 << KID_DISP_BITS) - 1)
-#define KID_MAX_TAXA ((int)KID_TAXON_MASK) /* all-ones is the build-time placeholder */
+#define KID_MAX_TAXA ((int)KID_TAXON_MASK)
 #define KID_MIN_LOG2_BUCKETS 22
 #define KID_MAX_LOG2_BUCKETS 32
 #define KID_MASK60 ((1ULL << 60) - 1ULL)
@@ -121,13 +122,6 @@ __device__ __forceinline__ uint32_t kid_lookup_from(const KidTableView &t, uint6
         if (r == 0) return 0;
     }
     return 0;
-}
-
-__device__ __forceinline__ uint32_t kid_gp(const KidTreeView &tr, uint32_t x, uint32_t &depth)
-{
-    uint2 n = __ldg(tr.node + x);
-    depth = n.y;
-    return n.x;
 }
 
 // Tree1::msca (:118-144): x if y is root or an ancestor-or-self of x; y if x is an ancestor of y;
