@@ -339,3 +339,24 @@ def test_trim_adversarial_qualities(layout):
     fin = _check_batch(gs, osamp, batch)
     _check_counts(gs, osamp)
     assert (fin == -1).sum() > 1000 and (fin >= 0).sum() > 1000
+
+
+def test_many_taxa_global_histogram_path(layout):
+    """More than 24 576 taxa: the per-block shared-memory gcount histogram no longer fits and the
+    kernels fall back to global atomics; also exercises taxon ids close to the 21-bit field limit of
+    the packed sectors."""
+    rng = np.random.default_rng(101)
+    n = 2_000_000  # taxa ids up to 2e6 (< 2^21)
+    parent = np.ones(n, np.int32)
+    inner = rng.integers(2, 1000, size=n)
+    parent[1000:] = inner[1000:]          # leaves hang off 998 inner nodes ...
+    parent[2:1000] = rng.integers(1, 2, size=998)  # ... which hang off the root
+    keys = H.canonical(rng.integers(0, 1 << 60, size=20000, dtype=np.uint64))
+    taxa = np.concatenate([rng.integers(1000, n, size=15000), rng.integers(2, 1000, size=5000)]).astype(np.uint32)
+    db = H.SynthDB(keys=keys, taxa=taxa, parent=parent)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db, layout)
+    batch = H.make_reads(rng, db, 2000)
+    fin = _check_batch(gs, osamp, batch)
+    _check_counts(gs, osamp)
+    assert fin.max() > 1_000_000
