@@ -122,6 +122,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def live_gather_ceiling(table_bytes):
+    """Independent random 32-byte reads per second on a buffer of the table's size
+    (tools/micro/gather_bench.cu, its own process, after the timed region): the practical ceiling
+    of any one-sector-per-lookup table.  (None, None) if the tool is not built."""
+    exe = os.path.join(ROOT, "tools", "micro", "gather_bench")
+    if not os.path.exists(exe):
+        return None, None
+    mib = max(1024, int(table_bytes) >> 20)
+    try:
+        r = subprocess.run([exe, str(mib), "4", "256", "8"], capture_output=True, text=True, timeout=120)
+        for line in r.stdout.splitlines():
+            if "G accesses/s" in line:
+                return float(line.split("ms")[1].split("G accesses/s")[0]), f"live: gather_bench {mib} MiB"
+    except Exception:
+        pass
+    return None, None
+
+
 def traffic_per_lookup():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
@@ -308,12 +326,15 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = lookups * SECTOR_BYTES / (kernel_ms / 1e3) / 1e9
     tr = traffic_per_lookup()
+    ceiling, ceiling_src = live_gather_ceiling(st["table_bytes"]) if world == 1 else (None, None)
+    if ceiling is None:
+        ceiling, ceiling_src = (tr or {}).get("gather_ceiling_gsectors_s"), "profiles/traffic.json"
     roofline = {"bound": "hbm", "kernel": "kid_classify2_kernel" if args.layout == "M" else "kid_classify_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tr["dram_bytes_per_lookup"] * lookups if tr else None),
                 "algorithmic_bytes_per_lookup": SECTOR_BYTES, "lookups_per_launch": lookups,
                 "kernel_ms": kernel_ms, "lookups_per_s": lookups / (kernel_ms / 1e3),
-                "random_sector_gather_ceiling_gsectors_s": (tr or {}).get("gather_ceiling_gsectors_s")}
+                "random_sector_gather_ceiling_gsectors_s": ceiling, "gather_ceiling_source": ceiling_src}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
