@@ -47,6 +47,10 @@ typedef struct kid_sample kid_sample; /* per-sample accumulators: gcount, seen f
 
 const char *kid_last_error(void);
 int kid_device_count(int *n);
+/* Creates the CUDA context of `device` (seconds on a large box).  Optional: kid_db_build does it on
+ * first use; a host calls this from a helper thread so that it overlaps reading the probe file
+ * (the reference spends that time in its 24 GiB table memset, newkmer_10nx.cpp:943,186-189). */
+int kid_device_init(int device);
 const char *kid_version(void);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 unsigned long long kid_kernel_launches(void);

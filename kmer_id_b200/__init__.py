@@ -36,6 +36,7 @@ _SIGS = {
     "kid_last_error": (C.c_char_p, []),
     "kid_version": (C.c_char_p, []),
     "kid_device_count": (_i, [C.POINTER(_i)]),
+    "kid_device_init": (_i, [_i]),
     "kid_kernel_launches": (C.c_ulonglong, []),
     "kid_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "kid_host_free": (None, [_vp]),

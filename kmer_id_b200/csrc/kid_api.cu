@@ -112,6 +112,18 @@ int kid_device_count(int *n)
     return KID_OK;
 }
 
+int kid_device_init(int device)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) return fail(KID_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= c) return fail(KID_EINVAL, "kid_device_init: device %d of %d", device, c);
+    DeviceGuard guard(device);
+    e = cudaFree(nullptr); // forces the primary context into existence
+    if (e != cudaSuccess) return fail(KID_ECUDA, "kid_device_init: %s", cudaGetErrorString(e));
+    return KID_OK;
+}
+
 unsigned long long kid_kernel_launches(void)
 {
     return __atomic_load_n(&g_kid_kernel_launches, __ATOMIC_RELAXED);

@@ -41,6 +41,15 @@ static inline bool is_ws(unsigned char c)
 }
 
 // process_kmer (:619-661): forward strand, upper-case ACGT only, every full 30-window
+static const struct BaseCodes {
+    uint8_t code[256];
+    BaseCodes()
+    {
+        for (int i = 0; i < 256; i++) code[i] = 0xFF;
+        code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3;
+    }
+} kBase;
+
 static inline void add_windows(const char *s, size_t n, uint32_t target, std::vector<uint64_t> &keys,
                                std::vector<uint32_t> &taxa)
 {
@@ -48,14 +57,8 @@ static inline void add_windows(const char *s, size_t n, uint32_t target, std::ve
     uint64_t kf = 0;
     int cpos = 0;
     for (size_t i = 0; i < n; i++) {
-        unsigned c;
-        switch (s[i]) {
-        case 'A': c = 0; break;
-        case 'C': c = 1; break;
-        case 'G': c = 2; break;
-        case 'T': c = 3; break;
-        default: cpos = 0; kf = 0; continue;
-        }
+        const unsigned c = kBase.code[(unsigned char)s[i]]; // table, not a switch: the bases are random
+        if (c > 3) { cpos = 0; kf = 0; continue; }
         kf = ((kf << 2) & mask) | c;
         if (++cpos == 30) {
             keys.push_back(kf);
@@ -83,19 +86,53 @@ bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
     if (len > 0 && line[len - 1] == '\r') len--; // :691-692
     if (len == 0) return false;                   // :693
     const char *p = line, *end = line + len;
-    // fast path: SEQ,uint,uint,uint,char,uint  - the format the builder writes
-    {
-        const char *s0 = p;
-        while (p < end && *p != ',' && !is_ws((unsigned char)*p)) p++;
-        const size_t slen = (size_t)(p - s0);
-        uint32_t target, org, pos, count;
-        if (slen > 0 && p < end && *p == ',' && (++p, fast_uint(p, end, target)) && p < end && *p == ',' &&
-            (++p, fast_uint(p, end, org)) && p < end && *p == ',' && (++p, fast_uint(p, end, pos)) &&
-            p < end && *p == ',' && p + 2 < end && p[1] != ',' && !is_ws((unsigned char)p[1]) &&
-            p[2] == ',' && (p += 3, fast_uint(p, end, count))) {
-            add_windows(s0, slen, target, keys, taxa);
+    // fast path: SEQ,uint,uint,uint,char,uint  - the format the builder writes.  One pass over SEQ
+    // makes the window keys (process_kmer :619-661); they are kept only if the rest of the line parses.
+    auto rest_ok = [&](const char *q, uint32_t &target) { // ",uint,uint,uint,char,uint" from the first comma
+        uint32_t org, pos, count;
+        return q < end && *q == ',' && (++q, fast_uint(q, end, target)) && q < end && *q == ',' &&
+               (++q, fast_uint(q, end, org)) && q < end && *q == ',' && (++q, fast_uint(q, end, pos)) &&
+               q < end && *q == ',' && q + 2 < end && q[1] != ',' && !is_ws((unsigned char)q[1]) &&
+               q[2] == ',' && (q += 3, fast_uint(q, end, count));
+    };
+    if (len > 31 && line[30] == ',') { // the usual line: exactly one 30-mer, two independent halves
+        uint64_t a = 0, b = 0;
+        unsigned bad = 0;
+        for (int i = 0; i < 15; i++) {
+            const unsigned ca = kBase.code[(unsigned char)line[i]], cb = kBase.code[(unsigned char)line[15 + i]];
+            bad |= ca | cb;
+            a = (a << 2) | ca;
+            b = (b << 2) | cb;
+        }
+        uint32_t target;
+        if (bad <= 3 && rest_ok(line + 30, target)) {
+            keys.push_back((a << 30) | b);
+            taxa.push_back(target);
             return true;
         }
+    }
+    {
+        const size_t k0 = keys.size();
+        const uint64_t mask = (1ULL << 60) - 1;
+        uint64_t kf = 0;
+        int cpos = 0;
+        for (; p < end; p++) {
+            const unsigned c = kBase.code[(unsigned char)*p];
+            if (c <= 3) {
+                kf = ((kf << 2) & mask) | c;
+                if (++cpos == 30) { keys.push_back(kf); cpos--; }
+                continue;
+            }
+            if (*p == ',' || is_ws((unsigned char)*p)) break;
+            cpos = 0; // any other character restarts the window
+            kf = 0;
+        }
+        uint32_t target;
+        if (p > line && rest_ok(p, target)) {
+            taxa.insert(taxa.end(), keys.size() - k0, target);
+            return true;
+        }
+        keys.resize(k0);
     }
     // slow path: the reference's own extraction sequence on the comma->blank line (:695-697)
     std::string l(line, len);

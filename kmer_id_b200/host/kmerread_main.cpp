@@ -9,6 +9,7 @@
 // apply_reference_probe_cap), no _reads.txt (commented out, :612-621).
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
+#include "device_warmup.hpp"
 #include "read_reader.hpp"
 
 #include <cstdio>
@@ -129,7 +130,9 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl;
 
     ProbeSet probes;
+    start_device_warmup(device); // CUDA context creation overlaps the parse
     load_probes_cached(pname, probes, /*target_signed=*/true);
+    finish_device_warmup();
     std::cout << probes.lines_parsed << " kmers loaded" << std::endl; // :1066
     if (probes.lines_parsed < 2) exit(1);                              // :1067
     // KID_REF_LOG2_CELLS: test hook - size of the reference table being replayed (MAXHASH, :41)

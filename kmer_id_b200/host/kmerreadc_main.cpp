@@ -9,6 +9,7 @@
 // Smith-Waterman branch and is ignored.
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
+#include "device_warmup.hpp"
 #include "read_reader.hpp"
 
 #include <cstdio>
@@ -173,7 +174,9 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl;
 
     ProbeSet probes;
+    start_device_warmup(device); // CUDA context creation overlaps the parse
     load_probes_cached(pname, probes, /*target_signed=*/false);
+    finish_device_warmup();
     std::cout << probes.lines_parsed << " kmers loaded" << std::endl;
     kid_db *db = nullptr;
     if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), num_targ, device,

@@ -11,6 +11,7 @@
 // probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
+#include "device_warmup.hpp"
 #include "read_reader.hpp"
 
 #include <chrono>
@@ -63,7 +64,7 @@ struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is 
 void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream *outread,
               std::vector<SavedRead> *saved)
 {
-    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 19, (size_t)96 << 20);
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, (size_t)48 << 20);
     std::vector<int32_t> taxon;
     std::vector<uint32_t> span;
     for (;;) {
@@ -124,7 +125,9 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl; // :984
 
     ProbeSet probes;
+    start_device_warmup(device); // CUDA context creation overlaps the parse
     const bool cached = load_probes_cached(pname, probes);
+    finish_device_warmup();
     const double t1 = now();
     kid_db *db = nullptr;
     if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), MAXTAR,

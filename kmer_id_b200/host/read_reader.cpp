@@ -8,6 +8,40 @@
 
 namespace kidhost {
 
+namespace {
+// Page-locking memory is slow (a fraction of a millisecond per MiB), and a run opens two readers per
+// sample: batch buffers go back to this process-wide list instead of to cudaFreeHost.
+std::mutex g_pinned_mu;
+std::vector<std::pair<void *, size_t>> g_pinned_free;
+
+void *pinned_get(size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        for (size_t i = 0; i < g_pinned_free.size(); i++)
+            if (g_pinned_free[i].second == bytes) {
+                void *p = g_pinned_free[i].first;
+                g_pinned_free[i] = g_pinned_free.back();
+                g_pinned_free.pop_back();
+                return p;
+            }
+    }
+    void *p = nullptr;
+    if (kid_host_alloc(&p, bytes) != 0) {
+        fprintf(stderr, "kmer_id_b200: %s\n", kid_last_error());
+        exit(1);
+    }
+    return p;
+}
+
+void pinned_put(void *p, size_t bytes)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.emplace_back(p, bytes);
+}
+} // namespace
+
 ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth)
     : fmt_(fmt), max_reads_(max_reads), max_bytes_(max_bytes)
 {
@@ -16,13 +50,8 @@ ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t
         auto b = std::make_unique<ReadBatch>();
         b->cap_bytes = max_bytes_ + kRefLineLimit;
         b->has_qual = fastq;
-        void *p = nullptr, *q = nullptr;
-        if (kid_host_alloc(&p, b->cap_bytes + 16) != 0 || (fastq && kid_host_alloc(&q, b->cap_bytes + 16) != 0)) {
-            fprintf(stderr, "kmer_id_b200: %s\n", kid_last_error());
-            exit(1);
-        }
-        b->seq = (uint8_t *)p;
-        b->qual = (uint8_t *)q;
+        b->seq = (uint8_t *)pinned_get(b->cap_bytes + 16);
+        b->qual = fastq ? (uint8_t *)pinned_get(b->cap_bytes + 16) : nullptr;
         free_.push_back(b.get());
         pool_.push_back(std::move(b));
     }
@@ -38,7 +67,7 @@ ReadBatchReader::~ReadBatchReader()
     }
     cv_.notify_all();
     if (th_.joinable()) th_.join();
-    for (auto &b : pool_) { kid_host_free(b->seq); kid_host_free(b->qual); }
+    for (auto &b : pool_) { pinned_put(b->seq, b->cap_bytes + 16); pinned_put(b->qual, b->cap_bytes + 16); }
 }
 
 ReadBatch *ReadBatchReader::get_free()

@@ -8,6 +8,7 @@
 #include "../../kmer_id_b200/host/db_loader.hpp"
 #include "../../kmer_id_b200/host/read_reader.hpp"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,7 @@ void kid_host_free(void *p) { free(p); }
 const char *kid_last_error(void) { return "host_dump stub"; }
 }
 
+#include "../../kmer_id_b200/host/gz_lines.hpp"
 using namespace kidhost;
 
 int main(int argc, char **argv)
@@ -54,6 +56,53 @@ int main(int argc, char **argv)
             if (last) break;
         }
         if (reader.open_failed()) printf("OPEN_FAILED\n");
+        return 0;
+    }
+    if (cmd == "loadtime") { // <probes.gz> <threads>: timing only
+        ProbeSet ps;
+        const auto t0 = std::chrono::steady_clock::now();
+        load_probes_gz(argv[2], ps, false, (unsigned)atoi(argv[3]));
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("lines %lld keys %zu in %.3f s\n", ps.lines_parsed, ps.keys.size(), dt);
+        return 0;
+    }
+    if (cmd == "readtime") { // <gz fastq>: timing only
+        const auto t0 = std::chrono::steady_clock::now();
+        ReadBatchReader reader(ReadFormat::GzFastq, argv[2], 1u << 20, 256u << 20, 3);
+        size_t n = 0, bytes = 0;
+        for (;;) {
+            ReadBatch *b = reader.next();
+            n += b->n;
+            bytes += b->off[b->n];
+            const bool last = b->last;
+            reader.recycle(b);
+            if (last) break;
+        }
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("%zu reads %zu bases in %.3f s = %.2f M reads/s\n", n, bytes, dt, n / dt / 1e6);
+        return 0;
+    }
+    if (cmd == "gunzip") { // <file> <threads> <piece_bytes> [out]: ParallelGunzip alone, min size 0
+        auto pg = ParallelGunzip::open(argv[2], (unsigned)atoi(argv[3]), (size_t)atoll(argv[4]), 0);
+        if (!pg) { fprintf(stderr, "NOT_APPLICABLE\n"); return 3; }
+        FILE *out = argc > 5 ? fopen(argv[5], "wb") : stdout;
+        const uint8_t *d;
+        size_t n;
+        int rc;
+        while ((rc = pg->next(d, n)) > 0) fwrite(d, 1, n, out);
+        if (out != stdout) fclose(out);
+        size_t a, b, c;
+        pg->piece_counts(a, b, c);
+        fprintf(stderr, "%s delivered %llu pieces %zu again %zu covered %zu\n", rc == 0 ? "END" : "GIVEUP",
+                (unsigned long long)pg->delivered(), a, b, c);
+        return rc == 0 ? 0 : 4;
+    }
+    if (cmd == "lines") { // <file> <threads> [out]: GzLineBlocks (parallel with zlib fallback)
+        GzLineBlocks src(argv[2], 4u << 20, (unsigned)atoi(argv[3]));
+        FILE *out = argc > 4 ? fopen(argv[4], "wb") : stdout;
+        std::vector<char> blk;
+        while (src.next(blk)) fwrite(blk.data(), 1, blk.size(), out);
+        if (out != stdout) fclose(out);
         return 0;
     }
     if (cmd == "tree") {

@@ -26,8 +26,10 @@ def _run_both(work, fq):
             p = os.path.join(fq, f)
             ref_files[f] = open(p, "rb").read()
             os.remove(p)
-    # default = R1 and R2 classified concurrently on two samples; KID_SERIAL=1 = one after the other
-    for env in ({}, {"KID_SERIAL": "1"}):
+    # default = R1 and R2 classified concurrently on two samples; KID_SERIAL=1 = one after the other;
+    # KID_GZ_*: force the multi-threaded inflater (host/pgz.cpp) onto these small files / switch it off
+    for env in ({}, {"KID_SERIAL": "1"}, {"KID_GZ_MIN_BYTES": "0", "KID_GZ_PIECE_BYTES": "8192", "KID_NO_CACHE": "1"},
+                {"KID_GZ_THREADS": "1"}):
         r_gpu = subprocess.run([NK_GPU, fq if fq.endswith("/") else fq + "/"], cwd=work, capture_output=True,
                                timeout=600, env=dict(os.environ, **env))
         assert r_gpu.returncode == 0, r_gpu.stderr.decode()
