@@ -159,7 +159,7 @@ bool parse_probe_line(const char *line, size_t len, std::vector<uint64_t> &keys,
 
 namespace {
 struct Block {
-    std::vector<char> text;
+    LineBlock text;
     std::vector<uint64_t> keys;
     std::vector<uint32_t> taxa;
     long long lines = 0;
@@ -186,16 +186,19 @@ void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed, 
                 b = todo.front();
                 todo.pop_front();
             }
-            const char *p = b->text.data(), *end = p + b->text.size();
             b->keys.reserve(b->text.size() / 48);
             b->taxa.reserve(b->text.size() / 48);
-            while (p < end) {
-                const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
-                if (!eol) break;
-                b->lines += parse_probe_line(p, (size_t)(eol - p), b->keys, b->taxa, target_signed);
-                p = eol + 1;
-            }
-            std::vector<char>().swap(b->text);
+            auto parse_lines = [&](const char *p, const char *end) {
+                while (p < end) {
+                    const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+                    if (!eol) break;
+                    b->lines += parse_probe_line(p, (size_t)(eol - p), b->keys, b->taxa, target_signed);
+                    p = eol + 1;
+                }
+            };
+            parse_lines(b->text.head.data(), b->text.head.data() + b->text.head.size());
+            parse_lines(b->text.body, b->text.body + b->text.body_len);
+            b->text = LineBlock(); // hands the inflated buffer back
             {
                 std::lock_guard<std::mutex> lk(mu);
                 b->done = true;
@@ -223,10 +226,19 @@ void load_probes_gz(const std::string &path, ProbeSet &out, bool target_signed, 
         }
     };
 
-    std::vector<char> text;
-    while (src.next(text)) {
+    // One key per ~50 bytes of text in the usual file; reserving address space up front (untouched
+    // pages cost nothing) saves the copies of a growing vector.  More keys than that just grow it.
+    {
+        struct stat st;
+        if (stat(path.c_str(), &st) == 0 && st.st_size > 0) {
+            const size_t guess = (size_t)st.st_size / 10 + 1024;
+            out.keys.reserve(out.keys.size() + guess);
+            out.taxa.reserve(out.taxa.size() + guess);
+        }
+    }
+    for (;;) {
         auto b = std::make_shared<Block>();
-        b->text.swap(text);
+        if (!src.next(b->text)) break;
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return todo.size() < 4 * threads; });

@@ -30,11 +30,22 @@ constexpr size_t kRefLineLimit = 0x4000; // BUFLEN, newkmer_10nx.cpp:85
     exit(255);
 }
 
+// A run of complete lines without copying the inflated bytes: `head` holds the line that straddles
+// the previous run and this one (empty if none), `body` the lines after it inside a buffer that
+// `keep` owns.  Every line still ends in '\n'.
+struct LineBlock {
+    std::vector<char> head;
+    const char *body = nullptr;
+    size_t body_len = 0;
+    std::shared_ptr<void> keep;
+    size_t size() const { return head.size() + body_len; }
+};
+
 class GzLineBlocks {
 public:
     // gz_threads: workers of the parallel inflater (pgz.hpp); 0 = default_gz_threads(), 1 = zlib only
     explicit GzLineBlocks(const std::string &path, size_t block_bytes = 4u << 20, unsigned gz_threads = 0)
-        : path_(path), zbuf_(block_bytes)
+        : path_(path), block_(block_bytes)
     {
         pgz_ = ParallelGunzip::open(path, gz_threads);
         if (!pgz_) open_zlib(0);
@@ -44,41 +55,64 @@ public:
         if (in_) gzclose(in_);
     }
     bool parallel() const { return pgz_ != nullptr; }
-    // Fills `out` with a run of complete lines (each still ending in '\n').  Returns false at
-    // end of stream.  The unterminated tail, if any, is dropped like the reference does.
-    bool next(std::vector<char> &out)
+
+    // Next run of complete lines.  Returns false at end of stream.  The unterminated tail of the
+    // stream, if any, is dropped like the reference does.
+    bool next(LineBlock &out)
     {
-        out.clear();
+        out.head.clear();
+        out.body = nullptr;
+        out.body_len = 0;
+        out.keep.reset();
         for (;;) {
             if (eof_) return false;
             const char *d;
             size_t n;
-            if (!fetch(d, n)) {
+            std::shared_ptr<void> keep;
+            if (!fetch(d, n, keep)) {
                 eof_ = true;
                 return false;
             }
-            const char *nl = (const char *)memrchr(d, '\n', n);
-            if (!nl) { // no complete line yet
+            const char *last = (const char *)memrchr(d, '\n', n);
+            if (!last) { // no complete line yet
                 carry_.insert(carry_.end(), d, d + n);
                 if (carry_.size() >= kRefLineLimit) ref_error("Buffer to small for input line lengths");
                 continue;
             }
-            const size_t upto = (size_t)(nl - d) + 1;
-            out.reserve(carry_.size() + upto);
-            out.assign(carry_.begin(), carry_.end());
-            out.insert(out.end(), d, d + upto);
-            carry_.assign(d + upto, d + n);
+            const char *body = d;
+            if (!carry_.empty()) { // finish the straddling line
+                const char *first = (const char *)memchr(d, '\n', n);
+                out.head.swap(carry_);
+                out.head.insert(out.head.end(), d, first + 1);
+                if (out.head.size() > kRefLineLimit) ref_error("Buffer to small for input line lengths");
+                body = first + 1;
+                carry_.clear();
+            }
+            out.body = body;
+            out.body_len = (size_t)(last + 1 - body);
+            out.keep = std::move(keep);
+            carry_.assign(last + 1, d + n);
             // every complete line must respect the reference's 16 KiB buffer: hop from a line start
             // to the last '\n' within the next 16 KiB - every line in between is shorter than that
-            for (size_t i = 0; i < out.size();) {
-                const size_t w = std::min(kRefLineLimit, out.size() - i);
-                const char *last = (const char *)memrchr(out.data() + i, '\n', w);
-                if (!last) ref_error("Buffer to small for input line lengths");
-                i = (size_t)(last - out.data()) + 1;
+            for (size_t i = 0; i < out.body_len;) {
+                const size_t w = std::min(kRefLineLimit, out.body_len - i);
+                const char *nl = (const char *)memrchr(body + i, '\n', w);
+                if (!nl) ref_error("Buffer to small for input line lengths");
+                i = (size_t)(nl - body) + 1;
             }
             if (carry_.size() >= kRefLineLimit) ref_error("Buffer to small for input line lengths");
             return true;
         }
+    }
+    // Same, copied into one contiguous vector.
+    bool next(std::vector<char> &out)
+    {
+        LineBlock b;
+        if (!next(b)) { out.clear(); return false; }
+        out.reserve(b.size());
+        out.assign(b.head.begin(), b.head.end());
+        out.insert(out.end(), b.body, b.body + b.body_len);
+        return true;
     }
 
 private:
@@ -87,25 +121,27 @@ private:
         in_ = gzopen(path_.c_str(), "rb");
         if (!in_) ref_error(nullptr); // gzread(NULL) < 0 -> error(gzerror(NULL)) prints an empty line
         gzbuffer(in_, 1u << 20);
+        std::vector<char> scratch(std::min<uint64_t>(skip, 1u << 20));
         while (skip) { // bytes the parallel inflater already delivered
-            const int got = gzread(in_, zbuf_.data(), (unsigned)std::min<uint64_t>(skip, zbuf_.size()));
+            const int got = gzread(in_, scratch.data(), (unsigned)std::min<uint64_t>(skip, scratch.size()));
             if (got <= 0) break; // the error (if any) shows again on the next read
             skip -= (uint64_t)got;
         }
     }
-    // next piece of the inflated stream; false at its end
-    bool fetch(const char *&d, size_t &n)
+    // next piece of the inflated stream, owned by `keep`; false at its end
+    bool fetch(const char *&d, size_t &n, std::shared_ptr<void> &keep)
     {
         if (pgz_) {
             const uint8_t *p;
-            const int rc = pgz_->next(p, n);
+            const int rc = pgz_->next(p, n, keep);
             if (rc > 0) { d = (const char *)p; return true; }
             if (rc == 0) return false;
             const uint64_t skip = pgz_->delivered(); // something zlib has to judge: let it
             pgz_.reset();
             open_zlib(skip);
         }
-        const int got = gzread(in_, zbuf_.data(), (unsigned)zbuf_.size());
+        auto buf = std::make_shared<std::vector<char>>(block_);
+        const int got = gzread(in_, buf->data(), (unsigned)buf->size());
         if (got < 0) {
             int err = 0;
             ref_error(gzerror(in_, &err));
@@ -115,15 +151,17 @@ private:
             in_ = nullptr;
             return false;
         }
-        d = zbuf_.data();
+        d = buf->data();
         n = (size_t)got;
+        keep = buf;
         return true;
     }
 
     std::string path_;
+    size_t block_;
     std::unique_ptr<ParallelGunzip> pgz_;
     gzFile in_ = nullptr;
-    std::vector<char> zbuf_, carry_;
+    std::vector<char> carry_;
     bool eof_ = false;
 };
 

@@ -522,7 +522,7 @@ struct ParallelGunzip::Impl {
     uint32_t run_crc = 0;
     uint64_t run_len = 0;
     bool in_member_data = false;
-    size_t holding = (size_t)-1;
+    std::shared_ptr<void> lent; // buffer behind the pointer the lending next() returned
 
     uint64_t piece_end_bit(size_t k) const { return (uint64_t)std::min(size, (k + 1) * piece_bytes) * 8; }
     size_t max_out() const { return (size_t)kMaxExpand * piece_bytes + (1u << 20); }
@@ -774,12 +774,14 @@ std::unique_ptr<ParallelGunzip> ParallelGunzip::open(const std::string &path, un
 
 int ParallelGunzip::next(const uint8_t *&out, size_t &len)
 {
+    return next(out, len, impl_->lent); // the previous run goes back to the pool here
+}
+
+int ParallelGunzip::next(const uint8_t *&out, size_t &len, std::shared_ptr<void> &keep)
+{
     Impl &s = *impl_;
+    keep.reset();
     if (s.failed) return -1;
-    if (s.holding != (size_t)-1) { // give the previous piece back
-        s.pieces[s.holding].drop_bytes();
-        s.holding = (size_t)-1;
-    }
     for (;;) {
         std::unique_lock<std::mutex> lk(s.mu);
         if (s.consumed == s.n_pieces) {
@@ -810,9 +812,12 @@ int ParallelGunzip::next(const uint8_t *&out, size_t &len)
             pc.drop_bytes();
             continue;
         }
-        s.holding = k;
         out = pc.bytes;
         len = pc.n_bytes;
+        const size_t cap = pc.cap_bytes;
+        keep = std::shared_ptr<void>(pc.bytes, [cap](void *p) { g_pool.put(p, cap); });
+        pc.bytes = nullptr;
+        pc.cap_bytes = 0;
         s.delivered += len;
         return 1;
     }

@@ -40,9 +40,12 @@ public:
     ParallelGunzip(const ParallelGunzip &) = delete;
     ParallelGunzip &operator=(const ParallelGunzip &) = delete;
 
-    // Next run of inflated bytes in stream order; the pointer stays valid until the next call.
+    // Next run of inflated bytes in stream order.
     // 1 = data, 0 = clean end of stream, -1 = give up (see above; delivered() says how much to skip).
+    // The first form lends the bytes until the next call; the second hands the buffer over (`keep`
+    // owns it), so that other threads can work on several runs while this one fetches the next.
     int next(const uint8_t *&data, size_t &len);
+    int next(const uint8_t *&data, size_t &len, std::shared_ptr<void> &keep);
     uint64_t delivered() const;
     // pieces accepted as first inflated / inflated again with known history / covered by a predecessor
     void piece_counts(size_t &as_found, size_t &again, size_t &covered) const;

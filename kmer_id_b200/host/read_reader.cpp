@@ -152,14 +152,13 @@ void ReadBatchReader::run(std::string path)
 void ReadBatchReader::run_gz_fastq(const std::string &path)
 {
     GzLineBlocks src(path);
-    std::vector<char> text;
+    LineBlock text;
     int mod4 = 0; // :768
     const char *seq = nullptr;
     size_t seqlen = 0;
-    std::string seq_carry, acc; // a record may straddle two text blocks
+    std::string seq_carry, acc; // a record may straddle two runs of lines
     bool seq_in_carry = false;
-    while (src.next(text)) {
-        const char *p = text.data(), *end = p + text.size();
+    auto lines = [&](const char *p, const char *end) {
         while (p < end) {
             const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
             size_t len = (size_t)(eol - p);
@@ -178,10 +177,14 @@ void ReadBatchReader::run_gz_fastq(const std::string &path)
             }
             p = eol + 1;
         }
-        if ((mod4 == 2 || mod4 == 3) && !seq_in_carry) { // the sequence line lives in `text`, about to go
+        if ((mod4 == 2 || mod4 == 3) && !seq_in_carry) { // the sequence line lives in this run, about to go
             seq_carry.assign(seq, seqlen);
             seq_in_carry = true;
         }
+    };
+    while (src.next(text)) {
+        lines(text.head.data(), text.head.data() + text.head.size());
+        lines(text.body, text.body + text.body_len);
     }
 }
 
@@ -213,10 +216,9 @@ void ReadBatchReader::run_plain_fastq(const std::string &path)
 void ReadBatchReader::run_gz_fasta(const std::string &path)
 {
     GzLineBlocks src(path);
-    std::vector<char> text;
+    LineBlock text;
     std::string sequence, acc;
-    while (src.next(text)) {
-        const char *p = text.data(), *end = p + text.size();
+    auto lines = [&](const char *p, const char *end) {
         while (p < end) {
             const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
             size_t len = (size_t)(eol - p);
@@ -232,6 +234,10 @@ void ReadBatchReader::run_gz_fasta(const std::string &path)
             }
             p = eol + 1;
         }
+    };
+    while (src.next(text)) {
+        lines(text.head.data(), text.head.data() + text.head.size());
+        lines(text.body, text.body + text.body_len);
     }
     if (sequence.length() > KID_KSIZE) emit(acc.data(), acc.size(), sequence.data(), sequence.size(), nullptr);
 }

@@ -9,6 +9,7 @@
 #include "../../kmer_id_b200/host/read_reader.hpp"
 
 #include <chrono>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -61,9 +62,13 @@ int main(int argc, char **argv)
     if (cmd == "loadtime") { // <probes.gz> <threads>: timing only
         ProbeSet ps;
         const auto t0 = std::chrono::steady_clock::now();
+        timespec c0, c1;
+        clock_gettime(CLOCK_THREAD_CPUTIME_ID, &c0);
         load_probes_gz(argv[2], ps, false, (unsigned)atoi(argv[3]));
+        clock_gettime(CLOCK_THREAD_CPUTIME_ID, &c1);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        printf("lines %lld keys %zu in %.3f s\n", ps.lines_parsed, ps.keys.size(), dt);
+        printf("lines %lld keys %zu in %.3f s (calling thread busy %.3f s)\n", ps.lines_parsed, ps.keys.size(), dt,
+               (double)(c1.tv_sec - c0.tv_sec) + 1e-9 * (double)(c1.tv_nsec - c0.tv_nsec));
         return 0;
     }
     if (cmd == "readtime") { // <gz fastq>: timing only

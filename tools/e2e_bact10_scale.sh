@@ -19,6 +19,7 @@ cd "$W"
 # whole file), so recompress with gzip itself before timing anything
 s=$(t)
 for f in bact10/probes10.txt.gz fq/big_R1_tr.fastq.gz fq/big_R2_tr.fastq.gz; do ( zcat "$f" | gzip -1 > "$f.one" && mv "$f.one" "$f" ) & done; wait
+ln -s big_R1_tr.fastq.gz fq/big2_R1_tr.fastq.gz; ln -s big_R2_tr.fastq.gz fq/big2_R2_tr.fastq.gz  # a second sample: steady-state time per sample
 say "recompress as single-member gzip -1: $(echo "$(t) - $s" | bc) s, $(du -sh bact10/probes10.txt.gz | cut -f1)"
 s=$(t); KID_NO_CACHE=1 KID_GZ_THREADS=1 KID_STATS=1 "$ROOT/kmer_id_b200/bin/nk10" "$W/fq/" > ours0.out 2> ours0.err; rc=$?; say "OURS (parse text DB, zlib inflate on one thread = round-1 path): rc=$rc wall $(echo "$(t) - $s" | bc) s"; cat ours0.err >> "$LOG"
 cp fq/big_result.txt zlib_result.txt
