@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-baseline-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files-e2e", action="store_true",
+                    help="skip the gz-files-on-disk -> _result.txt run of the nk10 drop-in")
     ap.add_argument("--layout", default="M", choices=["M", "K"], help="table layout (M = minimizer, default)")
     ap.add_argument("--log2-sectors", type=int, default=0, help="table size override (0 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=80.0,
@@ -355,11 +357,54 @@ def run_ours(args):
 
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(args, wl, dk, dt, parent, gcount_check=None)
+    if world == 1 and not args.no_files_e2e:
+        out["files_e2e"] = files_e2e(args)
     del dk, dt
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def files_e2e(args):
+    """SURVEY.md 8(d) "end-to-end (gz on disk -> _result.txt)": the shipped drop-in
+    kmer_id_b200/bin/nk10 on files, after the timed region, in its own process.  The probe DB in the
+    reference's text format at the benchmark's scale and three samples of gz FASTQ (generator's
+    multi-member gzip); times are nk10's own (KID_STATS).  None if the binaries are not built."""
+    import re
+    import shutil
+    import tempfile
+    nk10 = os.path.join(ROOT, "kmer_id_b200", "bin", "nk10")
+    synth = os.path.join(ROOT, "tools", "kid_synth")
+    if not (os.path.exists(nk10) and os.path.exists(synth)):
+        return None
+    pairs = min(args.pairs, 2_000_000)
+    work = tempfile.mkdtemp(prefix="kid_files_")
+    try:
+        fq = os.path.join(work, "fq")
+        subprocess.run([synth, "db", "--golden", GOLDEN_B10, "--out", work, "--den", str(args.db_den)], check=True,
+                       stdout=subprocess.DEVNULL)
+        for i in range(3):
+            subprocess.run([synth, "reads", "--golden", GOLDEN_B10, "--out", fq, "--sample", "s%d" % i, "--pairs",
+                            str(pairs), "--first-pair", str(i * pairs), "--den", str(args.db_den)], check=True,
+                           stdout=subprocess.DEVNULL)
+        t0 = time.perf_counter()
+        r = subprocess.run([nk10, fq + "/"], cwd=work, capture_output=True, text=True,
+                           env=dict(os.environ, KID_STATS="1", KID_NO_CACHE="1"))
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": "nk10 exited %d: %s" % (r.returncode, r.stderr[-300:])}
+        per_sample = [float(x) for x in re.findall(r"\[nk10\] s\d+: \d+ reads, \d+ lookups, \d+ hits in ([0-9.]+) s", r.stderr)]
+        m = re.search(r"\[nk10\] parse db ([0-9.]+) s, build table ([0-9.]+) s, total ([0-9.]+) s", r.stderr)
+        best = min(per_sample)
+        return {"value": pairs / best, "unit": UNIT,
+                "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, fastest of 3 samples "
+                        "(R1 and R2 inflated on all host cores, parsed, classified); probe DB parsed from gz text",
+                "pairs_per_sample": pairs, "sample_s": per_sample, "db_parse_s": float(m.group(1)),
+                "table_build_s": float(m.group(2)), "process_total_s": float(m.group(3)), "wall_s": wall,
+                "whole_run_pairs_per_s": 3 * pairs / wall, "host_cores": os.cpu_count()}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def cpu_baseline_port(args, wl, dk, dt, parent, gcount_check):

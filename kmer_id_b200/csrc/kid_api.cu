@@ -237,7 +237,6 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
     uint64_t *tmp_keys = nullptr;
     uint32_t *tmp_taxa = nullptr, *owner = nullptr;
     void *dstatus = nullptr;
-    (void)0;
     auto cleanup_tmp = [&]() {
         cudaFree(tmp_keys); cudaFree(tmp_taxa); cudaFree(owner); cudaFree(dstatus);
         tmp_keys = nullptr; tmp_taxa = nullptr; owner = nullptr; dstatus = nullptr;

@@ -208,6 +208,10 @@ def test_rejects_bad_inputs():
     b = H.make_reads(rng, db, 50)
     seq, qual = b.padded()
     assert (gs.classify(seq, qual, b.off) <= 0).all()
+    # context warm-up entry: fine on a real device, KID_EINVAL on one that does not exist
+    assert kid.lib.kid_device_init(0) == 0
+    assert kid.lib.kid_device_init(kid.device_count()) == -1
+    assert b"device" in kid.lib.kid_last_error()
 
 
 def test_build_is_deterministic(layout):
