@@ -171,15 +171,15 @@ struct Codes {
 
 const Codes &fixed_codes()
 {
-    static const Codes c = [] {
-        Codes f;
+    static const Codes &c = *[] { // leaked on purpose, see g_pool
+        Codes &f = *new Codes;
         uint8_t l[288];
         for (int s = 0; s < 288; s++) l[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
         build_table(l, 288, kLitRoot, kPay.lit, CodeUse::LitLen, f.lit);
         uint8_t d[32];
         memset(d, 5, sizeof d);
         build_table(d, 32, kDistRoot, kPay.dist, CodeUse::Dist, f.dist);
-        return f;
+        return &f;
     }();
     return c;
 }
@@ -287,7 +287,8 @@ private:
     std::mutex mu_;
     std::vector<std::pair<void *, size_t>> free_;
 };
-BlockPool g_pool;
+// Never destroyed: ref_error() may exit() while workers still decode into these buffers.
+BlockPool &g_pool = *new BlockPool;
 
 struct SymBuf { // kWin symbols of history, then the output
     uint16_t *p = nullptr;
