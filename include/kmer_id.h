@@ -55,7 +55,8 @@ const char *kid_version(void);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 unsigned long long kid_kernel_launches(void);
 /* page-locked host memory for the batch buffers handed to kid_classify_host (replaces the
- * per-line std::string of process_fqgz, newkmer_10nx.cpp:785) */
+ * per-line std::string of process_fqgz, newkmer_10nx.cpp:785).  Page-locked through the context of
+ * the device last named to kid_device_init / kid_db_build (device 0 before either), usable from all. */
 int kid_host_alloc(void **p, size_t bytes);
 void kid_host_free(void *p);
 

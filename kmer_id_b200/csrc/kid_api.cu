@@ -16,6 +16,10 @@ namespace {
 
 thread_local char g_err[512] = "";
 
+// device whose context page-locks host memory for kid_host_alloc: the last one a database was built
+// on or kid_device_init was called for (so that a host using GPU 3 does not wake GPU 0 for it)
+int g_host_alloc_device = 0;
+
 int fail(int code, const char *fmt, ...)
 {
     va_list ap;
@@ -121,6 +125,7 @@ int kid_device_init(int device)
     DeviceGuard guard(device);
     e = cudaFree(nullptr); // forces the primary context into existence
     if (e != cudaSuccess) return fail(KID_ECUDA, "kid_device_init: %s", cudaGetErrorString(e));
+    __atomic_store_n(&g_host_alloc_device, device, __ATOMIC_RELAXED);
     return KID_OK;
 }
 
@@ -133,6 +138,7 @@ int kid_host_alloc(void **p, size_t bytes)
 {
     if (!p) return fail(KID_EINVAL, "kid_host_alloc: p is NULL");
     *p = nullptr;
+    DeviceGuard guard(__atomic_load_n(&g_host_alloc_device, __ATOMIC_RELAXED));
     cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA, "cudaHostAlloc(%zu): %s", bytes,
@@ -202,6 +208,7 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
 
     DeviceGuard guard(device);
     if (!guard.ok) return fail(KID_ECUDA, "cudaSetDevice(%d) failed", device);
+    __atomic_store_n(&g_host_alloc_device, device, __ATOMIC_RELAXED);
     cudaStream_t stream = (cudaStream_t)stream_;
 
     const bool fixed = log2_sectors != 0;

@@ -3,6 +3,7 @@
 // the parse.  finish_device_warmup() joins (also at exit, so that no thread outlives main()).
 #pragma once
 #include <cstdlib>
+#include <functional>
 #include <thread>
 
 #include "../../include/kmer_id.h"
@@ -20,11 +21,14 @@ inline void finish_device_warmup()
     if (warmup_thread().joinable()) warmup_thread().join();
 }
 
-inline void start_device_warmup(int device)
+// `then` (optional) runs on the helper thread once the context exists, e.g. page-locking buffers
+inline void start_device_warmup(int device, std::function<void()> then = nullptr)
 {
     if (warmup_thread().joinable()) return;
     atexit(finish_device_warmup);
-    warmup_thread() = std::thread([device] { (void)kid_device_init(device); }); // errors resurface in kid_db_build
+    warmup_thread() = std::thread([device, then] {
+        if (kid_device_init(device) == 0 && then) then(); // errors resurface in kid_db_build
+    });
 }
 
 } // namespace kidhost

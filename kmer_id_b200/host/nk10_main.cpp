@@ -47,6 +47,8 @@ double now()
     exit(code);
 }
 
+constexpr size_t kBatchBytes = (size_t)48 << 20; // bases per batch handed to kid_classify_host
+
 struct SampleState {
     std::vector<int> gcount_host; // running copy, only to decide the first SAVENUM reads per taxon
     long long tct = 0;
@@ -64,7 +66,7 @@ struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is 
 void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream *outread,
               std::vector<SavedRead> *saved)
 {
-    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, (size_t)48 << 20);
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes);
     std::vector<int32_t> taxon;
     std::vector<uint32_t> span;
     for (;;) {
@@ -125,7 +127,8 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl; // :984
 
     ProbeSet probes;
-    start_device_warmup(device); // CUDA context creation overlaps the parse
+    // CUDA context creation and page-locking of the batch buffers overlap the parse
+    start_device_warmup(device, [] { prewarm_batch_buffers(kBatchBytes, getenv("KID_SERIAL") ? 1 : 2, true); });
     const bool cached = load_probes_cached(pname, probes);
     finish_device_warmup();
     const double t1 = now();

@@ -40,7 +40,20 @@ void pinned_put(void *p, size_t bytes)
     std::lock_guard<std::mutex> lk(g_pinned_mu);
     g_pinned_free.emplace_back(p, bytes);
 }
+size_t batch_buffer_bytes(size_t max_bytes) { return max_bytes + kRefLineLimit + 16; }
 } // namespace
+
+void prewarm_batch_buffers(size_t max_bytes, int readers, bool with_quality, int depth)
+{
+    const size_t bytes = batch_buffer_bytes(max_bytes);
+    std::vector<void *> got;
+    for (int i = 0; i < readers * depth * (with_quality ? 2 : 1); i++) {
+        void *p = nullptr;
+        if (kid_host_alloc(&p, bytes) != 0) break; // the reader reports the failure when it needs the buffer
+        got.push_back(p);
+    }
+    for (void *p : got) pinned_put(p, bytes);
+}
 
 ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth)
     : fmt_(fmt), max_reads_(max_reads), max_bytes_(max_bytes)
@@ -50,8 +63,8 @@ ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t
         auto b = std::make_unique<ReadBatch>();
         b->cap_bytes = max_bytes_ + kRefLineLimit;
         b->has_qual = fastq;
-        b->seq = (uint8_t *)pinned_get(b->cap_bytes + 16);
-        b->qual = fastq ? (uint8_t *)pinned_get(b->cap_bytes + 16) : nullptr;
+        b->seq = (uint8_t *)pinned_get(batch_buffer_bytes(max_bytes_));
+        b->qual = fastq ? (uint8_t *)pinned_get(batch_buffer_bytes(max_bytes_)) : nullptr;
         free_.push_back(b.get());
         pool_.push_back(std::move(b));
     }
@@ -67,7 +80,7 @@ ReadBatchReader::~ReadBatchReader()
     }
     cv_.notify_all();
     if (th_.joinable()) th_.join();
-    for (auto &b : pool_) { pinned_put(b->seq, b->cap_bytes + 16); pinned_put(b->qual, b->cap_bytes + 16); }
+    for (auto &b : pool_) { pinned_put(b->seq, batch_buffer_bytes(max_bytes_)); pinned_put(b->qual, batch_buffer_bytes(max_bytes_)); }
 }
 
 ReadBatch *ReadBatchReader::get_free()

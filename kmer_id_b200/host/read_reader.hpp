@@ -33,6 +33,10 @@ struct ReadBatch {
     bool last = false;        // no more batches after this one
 };
 
+// Page-locks the buffers that `readers` ReadBatchReaders of this max_bytes/depth will ask for and
+// parks them in the process-wide pool (read_reader.cpp); meant for a helper thread at start-up.
+void prewarm_batch_buffers(size_t max_bytes, int readers, bool with_quality, int depth = 3);
+
 class ReadBatchReader {
 public:
     // starts a background thread that inflates/parses `path` into batches of at most max_reads
