@@ -127,8 +127,10 @@ int main(int argc, char *argv[])
     std::cout << "tree loaded" << std::endl; // :984
 
     ProbeSet probes;
-    // CUDA context creation and page-locking of the batch buffers overlap the parse
-    start_device_warmup(device, [] { prewarm_batch_buffers(kBatchBytes, getenv("KID_SERIAL") ? 1 : 2, true); });
+    // CUDA context creation overlaps the parse.  (Page-locking the batch buffers here as well was
+    // measured and dropped: cudaHostAlloc and the parser's page faults fight over the address-space
+    // lock, and the load got 1-3 s slower to save 0.3 s on the first sample.)
+    start_device_warmup(device);
     const bool cached = load_probes_cached(pname, probes);
     finish_device_warmup();
     const double t1 = now();
