@@ -219,13 +219,18 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         B = lo;
         const double per_sector = layout == KID_LAYOUT_KEYHASH ? 1.0 : 0.45;
         while (B < hi && (double)((uint64_t)1 << B) * per_sector < (double)n_keys) B++;
-        // keep table + build scratch (owner array, sort buffers: ~44 B per sector + 36 B per key)
-        // inside the free device memory; a denser table only costs more second probes
+        // table + build scratch (owner array, sort buffers): ~44 B per sector + 36 B per key
+        const double slots = layout == KID_LAYOUT_KEYHASH ? 4.0 : (double)KID2_SLOTS_PER_SECTOR;
+        auto footprint = [&](int b) { return (double)((uint64_t)1 << b) * (32.0 + 4.0 * slots) + 36.0 * (double)n_keys; };
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const double slots = layout == KID_LAYOUT_KEYHASH ? 4.0 : (double)KID2_SLOTS_PER_SECTOR;
-            while (B > lo && (double)((uint64_t)1 << B) * (32.0 + 4.0 * slots) + 36.0 * (double)n_keys >
-                                 0.85 * (double)free_b &&
+            // layout M with memory to spare: half the load again.  A warp of 32 lookups then rarely
+            // has a lane that needs the second, dependent sector load (measured +3 % lookups/s at
+            // bact10 scale, 8.6 -> 17 GB of 180)
+            if (layout == KID_LAYOUT_MINIMIZER && B > lo && B < hi && footprint(B + 1) < 0.25 * (double)free_b) B++;
+            // keep table + scratch inside the free device memory; a denser table only costs more
+            // second probes
+            while (B > lo && footprint(B) > 0.85 * (double)free_b &&
                    (double)((uint64_t)1 << (B - 1)) * slots * 0.8 > (double)n_keys)
                 B--;
         }
