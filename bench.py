@@ -68,8 +68,8 @@ def workload_config(args, n_probes):
         "read_len": READ_LEN,
         "reads": "70% stitched from lineage probes, 0.5% subs, 0.1% N, 20% low-quality tails (seed 21)",
         "sharding": "reads sharded across ranks, table replicated",
-        "l2": "inputs_larger_than_l2 (%.1f GB of reads + %.1f GB table per step)"
-              % (args.pairs * 2 * READ_LEN * 2 / 1e9, 4.3 / max(1, args.db_den)),
+        "l2": "inputs_larger_than_l2 (%.1f GB of reads per step, GB-scale probe table: see table.bytes)"
+              % (args.pairs * 2 * READ_LEN * 2 / 1e9),
     }
 
 
