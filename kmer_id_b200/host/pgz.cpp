@@ -392,10 +392,16 @@ bool inflate_run(const uint8_t *data, size_t size, Bits &in, Run &run, size_t fl
                     if (back > pos - floor) return false; // before the member / before any history
                     uint16_t *dst = out + pos;
                     const uint16_t *src = dst - back;
-                    if (back >= 4) {
-                        for (uint32_t i = 0; i < len; i += 4) memcpy(dst + i, src + i, 8);
-                    } else {
-                        for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+                    if (back >= 8) { // 8 symbols at a time; most matches end with the first copy
+                        memcpy(dst, src, 16);
+                        for (uint32_t i = 8; i < len; i += 8) memcpy(dst + i, src + i, 16);
+                    } else { // overlapping run: the output is periodic with period `back`
+                        const uint32_t head = len < 16 ? len : 16;
+                        for (uint32_t i = 0; i < head; i++) dst[i] = src[i];
+                        if (len > 16) {
+                            const size_t eff = back * ((7 + back) / back); // multiple of the period, 8..14
+                            for (uint32_t i = 16; i < len; i += 8) memcpy(dst + i, dst + i - eff, 16);
+                        }
                     }
                     pos += len;
                     continue;
