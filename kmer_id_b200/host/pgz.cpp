@@ -358,37 +358,38 @@ bool inflate_run(const uint8_t *data, size_t size, Bits &in, Run &run, size_t fl
                 c = &dyn;
             }
             const uint32_t *lit = c->lit.data(), *dist = c->dist.data();
+            Bits b = in; // a local copy: the byte copies below may alias anything but this
             for (;;) {
                 if (pos + 320 > cap && !room(320)) return false;
-                in.refill();
-                if (in.p > in.end + 64) return false; // ran off the end of the file
-                uint32_t e = lit[in.buf & ((1u << kLitRoot) - 1)];
+                b.refill();
+                if (b.p > b.end + 64) return false; // ran off the end of the file
+                uint32_t e = lit[b.buf & ((1u << kLitRoot) - 1)];
                 if (e_kind(e) == K_SUB) {
-                    in.drop(kLitRoot);
-                    e = lit[e_val(e) + (in.buf & ((1u << e_extra(e)) - 1))];
+                    b.drop(kLitRoot);
+                    e = lit[e_val(e) + (b.buf & ((1u << e_extra(e)) - 1))];
                 }
-                in.drop((int)e_bits(e));
+                b.drop((int)e_bits(e));
                 const uint32_t k = e_kind(e);
                 if (k == K_LIT) {
                     out[pos++] = (uint16_t)e_val(e);
                     // a second literal from the same refill: >= 41 bits are left
-                    e = lit[in.buf & ((1u << kLitRoot) - 1)];
+                    e = lit[b.buf & ((1u << kLitRoot) - 1)];
                     if (e_kind(e) == K_LIT) {
-                        in.drop((int)e_bits(e));
+                        b.drop((int)e_bits(e));
                         out[pos++] = (uint16_t)e_val(e);
                     }
                     continue;
                 }
                 if (k == K_LEN) {
-                    const uint32_t len = e_val(e) + in.take((int)e_extra(e));
-                    uint32_t d = dist[in.buf & ((1u << kDistRoot) - 1)];
+                    const uint32_t len = e_val(e) + b.take((int)e_extra(e));
+                    uint32_t d = dist[b.buf & ((1u << kDistRoot) - 1)];
                     if (e_kind(d) == K_SUB) {
-                        in.drop(kDistRoot);
-                        d = dist[e_val(d) + (in.buf & ((1u << e_extra(d)) - 1))];
+                        b.drop(kDistRoot);
+                        d = dist[e_val(d) + (b.buf & ((1u << e_extra(d)) - 1))];
                     }
                     if (e_kind(d) != K_LEN) return false;
-                    in.drop((int)e_bits(d));
-                    const size_t back = e_val(d) + in.take((int)e_extra(d));
+                    b.drop((int)e_bits(d));
+                    const size_t back = e_val(d) + b.take((int)e_extra(d));
                     if (back > pos - floor) return false; // before the member / before any history
                     uint16_t *dst = out + pos;
                     const uint16_t *src = dst - back;
@@ -409,6 +410,7 @@ bool inflate_run(const uint8_t *data, size_t size, Bits &in, Run &run, size_t fl
                 if (k == K_EOB) break;
                 return false;
             }
+            in = b;
             if (in.pos() > size_bits) return false;
         }
         if (bfinal) {
