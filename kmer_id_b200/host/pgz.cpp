@@ -12,6 +12,8 @@
 #include <fcntl.h>
 #include <mutex>
 #include <sys/mman.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
 #include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
@@ -689,6 +691,11 @@ struct ParallelGunzip::Impl {
 
     void worker()
     {
+#ifdef __linux__
+        // The consumer of the inflated text (one parser thread per file) is the serial stage of the
+        // pipeline; when the machine is oversubscribed it, not these workers, should get the core.
+        setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 5);
+#endif
         for (;;) {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return stop || !resolve_q.empty() || (next_decode < n_pieces && next_decode < consumed + max_ahead); });

@@ -2,6 +2,7 @@
 #include "gz_lines.hpp"
 #include "../../include/kmer_id.h"
 
+#include <chrono>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -195,10 +196,18 @@ void ReadBatchReader::run_gz_fastq(const std::string &path)
             seq_in_carry = true;
         }
     };
-    while (src.next(text)) {
+    const bool stats = getenv("KID_READER_STATS") != nullptr; // where a reader thread spends its time
+    double t_wait = 0, t_parse = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    for (;;) {
+        const double t0 = stats ? now() : 0;
+        if (!src.next(text)) break;
+        const double t1 = stats ? now() : 0;
         lines(text.head.data(), text.head.data() + text.head.size());
         lines(text.body, text.body + text.body_len);
+        if (stats) { t_wait += t1 - t0; t_parse += now() - t1; }
     }
+    if (stats) fprintf(stderr, "[reader] %s: waited %.3f s for inflated text, parsed/copied for %.3f s\n", path.c_str(), t_wait, t_parse);
 }
 
 // kmer_read_m3.cpp:895-931 - getline, first blank-delimited token of each line
