@@ -356,7 +356,7 @@ def run_ours(args):
     }
 
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_port(args, wl, dk, dt, parent, gcount_check=None)
+        out["cpu_baseline"] = cpu_baseline_port(args, wl, dk, dt, parent, dout.cpu().numpy())
     if world == 1 and not args.no_files_e2e:
         out["files_e2e"] = files_e2e(args)
     del dk, dt
@@ -407,9 +407,10 @@ def files_e2e(args):
         shutil.rmtree(work, ignore_errors=True)
 
 
-def cpu_baseline_port(args, wl, dk, dt, parent, gcount_check):
+def cpu_baseline_port(args, wl, dk, dt, parent, gpu_taxa):
     """The CPU oracle (kind = "port"), one thread, on the first cpu_baseline_reads reads of the same
-    workload against the FULL probe table (so its cache behaviour is the real one)."""
+    workload against the FULL probe table (so its cache behaviour is the real one).  Its per-read
+    taxa double as a parity check of what the timed GPU steps computed for those reads."""
     import numpy as np
     from oracle import kor
     n = min(args.cpu_baseline_reads, 2 * args.pairs)
@@ -422,9 +423,13 @@ def cpu_baseline_port(args, wl, dk, dt, parent, gcount_check):
     off = wl.offsets(n)
     osamp = kor.OracleSample(odb)
     t0 = time.perf_counter()
-    osamp.classify(seq, qual, off)
+    fin, _ = osamp.classify(seq, qual, off)
     dt_s = time.perf_counter() - t0
-    return {"value": (n / 2) / dt_s, "unit": UNIT, "cores": 1, "kind": "port",
+    if not np.array_equal(fin, gpu_taxa[:n]):
+        bad = int(np.flatnonzero(fin != gpu_taxa[:n])[0])
+        raise SystemExit("bench.py: GPU and oracle disagree on read %d of the benchmark batch: %d vs %d"
+                         % (bad, int(gpu_taxa[bad]), int(fin[bad])))
+    return {"value": (n / 2) / dt_s, "unit": UNIT, "cores": 1, "kind": "port", "parity_checked_reads": int(n),
             "sample": "first %d reads of rank 0's batch, full %d-probe table, oracle/kid_oracle.c" % (n, keys.size),
             "lookups_per_s": osamp.lookups / dt_s, "seconds": dt_s}
 
