@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
+constexpr int kWarpsPerBlock = KID_CLASSIFY1_THREADS / 32;
 constexpr int kWindowStarts = 448; // k-mer starts served per window: 15 + 447 + 29 < 512
 constexpr int kCodeWords = 36;     // 32 + slack for the 3-word read at the window end
 constexpr int kValidWords = 20;    // 16 + slack
@@ -49,7 +49,7 @@ __device__ __forceinline__ void pack4(uint32_t x, bool accept_u, uint32_t &code8
 }
 
 template <bool HAS_QUAL, bool SMEM_HIST>
-__global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 3)
+__global__ void __launch_bounds__(KID_CLASSIFY1_THREADS, 3)
 kid_classify_kernel(const KidClassifyParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -257,7 +257,7 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
         if (err != cudaSuccess) return err;
     }
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KID_CLASSIFY_THREADS, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KID_CLASSIFY1_THREADS, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     // persistent grid: a whole number of resident waves, but never more warps than reads
@@ -265,7 +265,7 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
     const size_t need = (p.n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > need) blocks = need;
     if (blocks == 0) return cudaSuccess;
-    kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
+    kern<<<(unsigned)blocks, KID_CLASSIFY1_THREADS, smem, stream>>>(p);
     KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }

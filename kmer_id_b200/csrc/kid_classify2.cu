@@ -489,6 +489,14 @@ cudaError_t launch_one(const KidClassifyParams &p, int sm_count, cudaStream_t st
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KID_CLASSIFY_THREADS, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
+    // shared memory and L1 are one 256 KB array: reserve only what the resident blocks use, the
+    // rest caches the read stream, the taxonomy rows and the spill slots
+    if (getenv("KID_NO_CARVEOUT") == nullptr) {
+        const size_t need = (size_t)per_sm * (smem + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct); // a hint: failure is harmless
+    }
     size_t blocks = (size_t)sm_count * per_sm; // persistent: a whole number of resident waves
     const size_t need = ((p.n_reads + kGroup - 1) / kGroup + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > need) blocks = need;
@@ -515,16 +523,13 @@ cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaS
 #ifdef KID_TUNE_VARIANTS // experiment builds only: pick the variant with KID_TUNE=<n>
     static const int tune = getenv("KID_TUNE") ? atoi(getenv("KID_TUNE")) : 0;
     switch (tune) {
-    case 1: return launch_variant<4, 2>(p, sm_count, stream);
-    case 2: return launch_variant<4, 3>(p, sm_count, stream);
-    case 3: return launch_variant<2, 5>(p, sm_count, stream);
-    case 4: return launch_variant<2, 3>(p, sm_count, stream);
-    case 5: return launch_variant<1, 5>(p, sm_count, stream);
-    case 6: return launch_variant<3, 3>(p, sm_count, stream);
+    case 1: return launch_variant<1, 1024 / KID_CLASSIFY_THREADS>(p, sm_count, stream);
+    case 2: return launch_variant<3, 1024 / KID_CLASSIFY_THREADS>(p, sm_count, stream);
+    case 3: return launch_variant<4, 1024 / KID_CLASSIFY_THREADS>(p, sm_count, stream);
     default: break;
     }
 #endif
-    // measured on B200 (tools/run_tune.sh): 2 chunks in flight at 4 blocks/SM (64 registers) beats
-    // 4 chunks at 3 blocks/SM by 27 % - the kernel is issue/latency bound, not DRAM bound
-    return launch_variant<2, 4>(p, sm_count, stream);
+    // measured on B200 (tools/run_tune.sh): 2 chunks in flight at 32 warps/SM (64 registers) beats
+    // 4 chunks at 24 warps/SM by 27 % - the kernel is issue/latency bound, not DRAM bound
+    return launch_variant<2, 1024 / KID_CLASSIFY_THREADS>(p, sm_count, stream); // 64 registers per thread
 }

@@ -4,7 +4,14 @@
 #include "kid_table2.cuh"
 
 #define KID_KSIZE 30
-#define KID_CLASSIFY_THREADS 256
+// Layout M kernel: one 1024-thread block per SM at 64 registers per thread.  Measured on B200 with
+// the same 32 resident warps per SM: 4 x 256 threads 99.7 G lookups/s, 2 x 512 104.7 G, 1 x 1024
+// 112.3 G (768 threads at 80 registers: 97.2 G) - one shared-memory gcount histogram per SM instead
+// of four leaves more of the 256 KB array to L1.
+#ifndef KID_CLASSIFY_THREADS
+#define KID_CLASSIFY_THREADS 1024
+#endif
+#define KID_CLASSIFY1_THREADS 256 // layout K kernel (bake-off only)
 #define KID_SMEM_HIST_MAX_BYTES (96u * 1024u) /* gcount histogram lives in smem up to 24576 taxa */
 
 enum KidLayout { KID_LAYOUT_MINIMIZER = 0, KID_LAYOUT_KEYHASH = 1 };
