@@ -6,7 +6,7 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall $(if $(TUNE),-DKID_TUNE_VARIANTS) $(if $(THREADS),-DKID_CLASSIFY_THREADS=$(THREADS))
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall $(if $(TUNE),-DKID_TUNE_VARIANTS) $(if $(THREADS),-DKID_CLASSIFY_THREADS=$(THREADS)) $(if $(MINBLOCKS),-DKID_CLASSIFY_MINBLOCKS=$(MINBLOCKS))
 CXXFLAGS  := -O3 -std=c++17 -Wall -Wextra -fPIC -pthread
 CUDA_HOME ?= /usr/local/cuda
 

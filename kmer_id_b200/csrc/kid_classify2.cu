@@ -531,5 +531,8 @@ cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaS
 #endif
     // measured on B200 (tools/run_tune.sh): 2 chunks in flight at 32 warps/SM (64 registers) beats
     // 4 chunks at 24 warps/SM by 27 % - the kernel is issue/latency bound, not DRAM bound
-    return launch_variant<2, 1024 / KID_CLASSIFY_THREADS>(p, sm_count, stream); // 64 registers per thread
+#ifndef KID_CLASSIFY_MINBLOCKS
+#define KID_CLASSIFY_MINBLOCKS (1024 / KID_CLASSIFY_THREADS) // 32 warps per SM at 64 registers per thread
+#endif
+    return launch_variant<2, KID_CLASSIFY_MINBLOCKS>(p, sm_count, stream);
 }
