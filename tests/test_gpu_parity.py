@@ -364,3 +364,35 @@ def test_many_taxa_global_histogram_path(layout):
     fin = _check_batch(gs, osamp, batch)
     _check_counts(gs, osamp)
     assert fin.max() > 1_000_000
+
+
+def test_hot_gcount_bin():
+    """All reads of a large batch end in ONE gcount bin (7 M reads with no hit -> bin 0; 7 M copies of a
+    read that hits one probe -> one leaf bin): the per-block shared-memory histograms and their
+    flush must not lose or wrap counts (> 40 000 increments of one counter per block)."""
+    import torch
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(77)
+    db = H.make_db(rng, 500)
+    gdb = kid.Database(db.keys, db.taxa, db.parent)
+    n, L = 7_000_000, 31
+    dev = torch.device("cuda:0")
+    off = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    # (a) poly-A reads: one k-mer each, not in the table
+    s = kid.Sample(gdb)
+    seq = torch.full((n * L + 64,), ord("A"), dtype=torch.uint8, device=dev)
+    s.classify_device(seq, None, off, n, out, None, 0)
+    g, u = s.counts()
+    assert g[0] == n and g.sum() == n and u.sum() == 0
+    # (b) every read is probe 7 followed by one base: two k-mers, the first one hits
+    t = int(db.taxa[7])
+    assert t > 1
+    one = np.concatenate([H.key_to_bases(int(db.keys[7])), np.frombuffer(b"A", np.uint8)]).astype(np.uint8)
+    seq[: n * L] = torch.from_numpy(np.tile(one, n)).to(dev)
+    s.begin()
+    s.classify_device(seq, None, off, n, out, None, 0)
+    g, u = s.counts()
+    v = int(out[0])  # every read is the same read: t, unless its second k-mer happens to hit as well
+    assert v > 1 and g[v] == n and g.sum() == n and bool((out == v).all())
+    assert u[t] == 1
