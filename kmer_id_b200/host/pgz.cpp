@@ -670,22 +670,26 @@ struct ParallelGunzip::Impl {
                 for (size_t i = 0; i < r.n; i++)
                     if (s[i] >= 256 && s[i] < lowest) return false;
             }
-            for (size_t i = 0; i < r.n; i++) pc.bytes[i] = lut[s[i]];
+            // bytes and their CRC-32 in one sweep, 64 KiB at a time, so that the CRC reads the cache
+            constexpr size_t kTile = 64u << 10;
+            size_t from = 0;
+            auto sweep = [&](size_t to, bool ends_member, uint32_t want_crc, uint32_t want_isize) {
+                uint32_t crc = 0;
+                for (size_t a = from; a < to; a += kTile) {
+                    const size_t b = std::min(to, a + kTile);
+                    for (size_t i = a; i < b; i++) pc.bytes[i] = lut[s[i]];
+                    crc = (uint32_t)crc32_z(crc, pc.bytes + a, b - a);
+                }
+                pc.segs.push_back(Segment{to - from, crc, ends_member, want_crc, want_isize});
+                from = to;
+            };
+            for (const MemberEnd &me : r.ends) sweep(me.out_pos, true, me.crc, me.isize);
+            if (from < r.n) sweep(r.n, false, 0, 0);
+        } else {
+            for (const MemberEnd &me : r.ends) pc.segs.push_back(Segment{0, 0, true, me.crc, me.isize});
         }
         r.sym.release();
         std::vector<uint8_t>().swap(pc.window);
-        size_t from = 0;
-        for (const MemberEnd &me : r.ends) {
-            Segment sg;
-            sg.len = me.out_pos - from;
-            sg.crc = (uint32_t)crc32_z(0, pc.bytes + from, sg.len);
-            sg.ends_member = true;
-            sg.want_crc = me.crc;
-            sg.want_isize = me.isize;
-            pc.segs.push_back(sg);
-            from = me.out_pos;
-        }
-        if (from < r.n) pc.segs.push_back(Segment{r.n - from, (uint32_t)crc32_z(0, pc.bytes + from, r.n - from), false, 0, 0});
         return true;
     }
 
