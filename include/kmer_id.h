@@ -71,6 +71,9 @@ void kid_host_free(void *p);
  *   keys_on_device    non-zero if keys/taxa are device pointers (then they are read in place).
  *   log2_sectors      0 = size the table from n_keys; else log2 of the number of 32-byte sectors
  *                     (layout M: 12..32, layout K: 22..32).
+ * Environment (tuning/test knob): KID_DB_SUB_BITS=2|3|4 forces how many sectors (4, 8, 16) one
+ * minimizer addresses in layout M; by default 4, and 8 or 16 only for databases beyond 4e8 keys
+ * that device memory keeps densely packed (kid_table2.cuh).
  */
 int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
                  const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_sectors,

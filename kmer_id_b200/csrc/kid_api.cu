@@ -69,6 +69,7 @@ struct kid_db {
     int log2_sectors = 0;
     int sm_count = 148;
     int max_probe = 0;
+    int sub_bits = 2;           // layout M: log2(sectors per minimizer-addressed group)
     unsigned flags = 0;
     uint64_t n_sectors = 0;     // addressable home sectors of 32 bytes (K: 4 slots each, M: 3 entries each)
     uint64_t total_sectors = 0; // n_sectors + slack (clusters run past the last home sector, no wrap)
@@ -80,7 +81,7 @@ struct kid_db {
     uint64_t n_slots() const { return (layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR) * total_sectors; }
     const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
     KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
-    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - 2), max_probe }; }
+    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - sub_bits), max_probe, sub_bits }; }
     KidTreeView tree_view() const { return KidTreeView{ tree, n_taxa }; }
 };
 
@@ -236,6 +237,22 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         }
     }
 
+    // several 1e8 keys and more than ~1.5 of them per 128-byte line (memory kept the table small):
+    // the m = 16 minimizers saturate, spread each over 2 or 4 lines (kid_table2.cuh).  KID_DB_SUB_BITS overrides.
+    int sub_bits = 2;
+    if (layout == KID_LAYOUT_MINIMIZER) {
+        const double per_line = (double)n_keys * 4.0 / (double)((uint64_t)1 << B);
+        if (n_keys > 400000000ull) { // below that the minimizers are far from saturated
+            if (per_line > 3.0) sub_bits = 4;
+            else if (per_line > 1.5) sub_bits = 3;
+        }
+        if (const char *e = getenv("KID_DB_SUB_BITS")) {
+            const int v = atoi(e);
+            if (v >= 2 && v <= 4) sub_bits = v;
+        }
+        if (sub_bits > B - 2) sub_bits = 2; // tiny tables
+    }
+
     kid_db *db = new (std::nothrow) kid_db;
     if (!db) return fail(KID_ENOMEM, "kid_db_build: host allocation failed");
     db->device = device;
@@ -282,7 +299,8 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         bp.slots_per_sector = layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR;
         bp.n_sectors = n_sectors;
         bp.slack_sectors = layout == KID_LAYOUT_KEYHASH ? KID1_SLACK_SECTORS : KID2_SLACK_SECTORS;
-        bp.line_shift = 32 - (B - 2);
+        bp.sub_bits = sub_bits;
+        bp.line_shift = 32 - (B - sub_bits);
         bp.rem_bits = 60 - B;
         bp.n_taxa = (uint32_t)n_taxa;
         bp.max_taxon = layout == KID_LAYOUT_KEYHASH ? (uint32_t)KID_MAX_TAXA : (uint32_t)KID2_MAX_TAXA;
@@ -306,6 +324,7 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
             }
             KID_CUDA_B(cudaStreamSynchronize(stream));
             db->log2_sectors = B;
+            db->sub_bits = sub_bits;
             db->n_sectors = n_sectors;
             db->total_sectors = total_sectors;
             db->n_distinct = st.n_distinct;

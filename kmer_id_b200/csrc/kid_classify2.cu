@@ -259,8 +259,8 @@ __device__ __forceinline__ void scan_kmers(const KidClassifyParams &p, const Kid
                 const int j = c + 32 * u + lane, t = tbase + j;
                 act[u] = (int32_t)(strip.kmask[t >> 5] << (t & 31)) < 0 && (unsigned)(j - first) <= (unsigned)(last - first);
                 lane_lookups += act[u]; // each is one getHash call (:529); summed over lanes at the end
-                const uint32_t line = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
-                sec[u] = (line << 2) | kid_key_sector(key[u]);
+                const uint32_t grp = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
+                sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
                 kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
             }
         }

@@ -54,7 +54,8 @@ struct KidSortedBuildParams {
     int slots_per_sector;  // 4 (K) or 3 (M)
     uint64_t n_sectors;    // addressable home sectors (power of two)
     uint64_t slack_sectors; // extra sectors after the last home sector (no wrap-around)
-    int line_shift;        // layout M: 32 - log2_lines
+    int line_shift;        // layout M: 32 - log2(groups)
+    int sub_bits;          // layout M: log2(sectors per minimizer-addressed group), 2..4
     int rem_bits;          // layout K: 60 - log2_sectors
     uint32_t n_taxa, max_taxon, max_disp;
 };

@@ -10,7 +10,7 @@
 //   c(i)     = kid_mm_hash(canonical 16-mer starting at base i)        i = 0..14 within the 30-mer
 //   M(key)   = min_i c(i)                                              strand independent
 //   line     = (M * 0x9E3779B1) >> (32 - L)                            2^L lines of 128 bytes
-//   sector   = 4 * line + kid_key_sector(key)                          4 sectors per line
+//   sector   = 4 * line + top 2 bits of kid_key_hash32(key)            4 sectors per line
 //   sector   = 3 entries: words 0..5 = three 64-bit keys (key | 1<<63, 0 = empty), words 6..7 =
 //              three 21-bit taxa; 12 entries per 128-byte line
 // Adjacent k-mers of a read share their minimizer in runs of ~7.5, so the 32 lanes of a warp (32
@@ -39,8 +39,9 @@
 struct Kid2TableView {
     const uint4 *sectors; // 2 uint4 (= 32 bytes, 3 entries) per sector
     uint64_t sector_mask; // n_sectors - 1 (home sectors; the table has slack sectors after them)
-    int line_shift;       // 32 - log2_lines
+    int line_shift;       // 32 - log2(groups): the minimizer picks a group of 2^sub_bits sectors
     int max_probe;        // longest displacement (in sectors) any key needed at build time
+    int sub_bits;         // 2 = one 128-byte line per minimizer (default); 3, 4 for very large DBs
 };
 
 // reverse complement of a 16-mer held in 32 bits (first base in the top pair)
@@ -92,16 +93,21 @@ __host__ __device__ __forceinline__ uint32_t kid_minimizer(uint64_t key)
     return m;
 }
 
-__host__ __device__ __forceinline__ uint32_t kid_key_sector(uint64_t key)
+// the key's own hash picks the sector inside the minimizer's group: its top sub_bits bits
+__host__ __device__ __forceinline__ uint32_t kid_key_hash32(uint64_t key)
 {
-    return (((uint32_t)key ^ (uint32_t)(key >> 32)) * 0xC2B2AE35u) >> 30;
+    return ((uint32_t)key ^ (uint32_t)(key >> 32)) * 0xC2B2AE35u;
 }
 
+// sub_bits = log2(sectors per minimizer-addressed group).  2 = one 128-byte line, which is what keeps
+// neighbouring k-mers of a read on one DRAM line.  With m = 16 only ~10 % of the 2^31 canonical
+// 16-mers ever win a 15-way minimum, so beyond ~3e8 keys several keys per minimizer pile into one
+// 12-entry line; 3 or 4 spreads a minimizer over 2 or 4 lines instead.
 __host__ __device__ __forceinline__ uint64_t kid2_home_sector(uint32_t minimizer, uint64_t key,
-                                                              int line_shift)
+                                                              int line_shift, int sub_bits)
 {
-    const uint32_t line = line_shift >= 32 ? 0u : (minimizer * 0x9E3779B1u) >> line_shift;
-    return ((uint64_t)line << 2) | kid_key_sector(key);
+    const uint32_t grp = line_shift >= 32 ? 0u : (minimizer * 0x9E3779B1u) >> line_shift;
+    return ((uint64_t)grp << sub_bits) | (kid_key_hash32(key) >> (32 - sub_bits));
 }
 
 #ifdef __CUDACC__

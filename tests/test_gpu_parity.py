@@ -396,3 +396,21 @@ def test_hot_gcount_bin():
     v = int(out[0])  # every read is the same read: t, unless its second k-mer happens to hit as well
     assert v > 1 and g[v] == n and g.sum() == n and bool((out == v).all())
     assert u[t] == 1
+
+
+@pytest.mark.parametrize("sub_bits", [3, 4])
+def test_wide_minimizer_groups(sub_bits, monkeypatch):
+    """Layout M for very large databases: a minimizer addresses 2 or 4 lines instead of one
+    (kid_table2.cuh sub_bits; chosen automatically beyond 4e8 keys, forced here).  Same results,
+    also on a table loaded so high that keys get displaced."""
+    monkeypatch.setenv("KID_DB_SUB_BITS", str(sub_bits))
+    rng = np.random.default_rng(300 + sub_bits)
+    db = H.make_db(rng, 6000, n_dup=200, n_zero=50)
+    odb, osamp = _oracle(db)
+    for kw in ({}, {"log2_sectors": 12}):  # default size, and 4096 sectors for ~5800 keys
+        gdb, gs = _gpu(db, LAYOUT_M, **kw)
+        want = np.array([odb.lookup(int(k)) for k in db.keys[:2000]], dtype=np.uint32)
+        assert np.array_equal(gdb.lookup(db.keys[:2000]), want)
+        osamp.reset()
+        _check_batch(gs, osamp, H.make_reads(rng, db, 3000, ragged=True))
+        _check_counts(gs, osamp)
