@@ -15,7 +15,9 @@ classified reads.
   e2e    the same through kid_classify_host from pinned HOST buffers (H2D + D2H inside the region)
   roofline.achieved = lookups/launch x 32 B / mean classify-kernel time  (32 B = one DRAM sector per
            lookup); peak = MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline: the CPU oracle (a port, oracle/kid_oracle.c) single-threaded on a bounded sample
+  cpu_baseline: the CPU oracle (a port, oracle/kid_oracle.c) single-threaded on a bounded sample;
+           its per-read taxa are compared with the GPU's for the same reads (parity_checked_reads)
+  files_e2e    gz FASTQ files on disk -> _result.txt through kmer_id_b200/bin/nk10 (N = 1 only)
 
 Prints ONE JSON line on rank 0.
 """
