@@ -162,3 +162,24 @@ def test_line_blocks_fall_back_like_zlib(tmp_path, texts):
         rc1, _, err1 = _lines(p, 1, small)
         rc8, _, err8 = _lines(p, 8, small)
         assert rc1 == 255 and rc8 == 255 and err1 == err8 and err1.strip(), (name, err1, err8)
+
+
+def test_lines_longer_than_a_piece(tmp_path):
+    """Lines of up to 15 KB (under the reference's 16 KiB limit) with 1-KiB... 4-KiB inflated pieces: one
+    line is assembled from several pieces, and blank lines / CRLF survive untouched."""
+    rng = np.random.default_rng(123)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)
+    parts = []
+    for i in range(400):
+        parts.append(b">contig%d\n" % i)
+        parts.append(bases[rng.integers(0, 4, int(rng.integers(1, 15000)))].tobytes() + (b"\r\n" if i % 3 == 0 else b"\n"))
+        if i % 7 == 0:
+            parts.append(b"\n")
+    raw = b"".join(parts)
+    p = str(tmp_path / "long.gz")
+    with open(p, "wb") as f:
+        f.write(gzip.compress(raw, 6))
+    env = {"KID_GZ_MIN_BYTES": "0", "KID_GZ_PIECE_BYTES": "1024"}
+    rc1, one, _ = _lines(p, 1, env)
+    rc8, many, _ = _lines(p, 8, env)
+    assert rc1 == 0 and rc8 == 0 and one == raw and many == raw
