@@ -3,14 +3,15 @@
 // Replaces, for a whole batch of reads, process_qual (newkmer_10nx.cpp:714-760), process_read
 // (:452-617), Hashtable::getHash (:204-233) and Tree1::msca (:118-144).
 //
-// Persistent grid; a warp works on one read at a time and lane j of chunk c owns the k-mer that
-// starts at base 32c+j of that read.
+// Persistent grid, one 1024-thread block per SM (kid_kernels.cuh); a warp works on one read at a
+// time and lane j of chunk c owns the k-mer that starts at base 32c+j of that read.
 //   GROUP   a warp takes kGroup (3) consecutive reads at a time; when they fit one 512-base window
 //           (always for 150-bp reads) they are loaded, packed and masked ONCE, which cuts the
 //           per-read prologue by ~2/3.  Longer reads take the one-read-at-a-time path (windows of
 //           448 k-mer starts).
 //   LOAD    as soon as the offsets are known the warp issues, together, the coalesced 128-bit
-//           loads of the bases and 32-byte loads of every read's first/last quality bytes.
+//           loads of the bases (streaming: L1::no_allocate) and 32-byte loads of every read's
+//           first/last quality bytes.
 //   TRIM    the four `while` loops of process_qual (:727-753) are "first/last position with a
 //           property" searches; the common case is answered from the two preloaded quality
 //           registers with ballots and shuffles, the rest by a 32-positions-per-step scan.
@@ -20,8 +21,8 @@
 //           32 are its 16-mer (minimizer candidate), the top 60 its forward k-mer (:481-517);
 //           __brevll gives the reverse complement, min() the canonical key (:528).
 //   MINIM   sliding minimum of the 16-mer hashes over 15 positions with 4 shuffle rounds
-//           (1,2,4,7) across 4 chunks + a 14-lane halo: M(key) without looking at the key.
-//   LOOKUP  sector = 4*line(M) + sector(key); four chunks (128 k-mers) request their 32-byte
+//           (1,2,4,7) across kUnroll (2) chunks + a 14-lane halo: M(key) without looking at the key.
+//   LOOKUP  sector = 4*line(M) + sector(key); kUnroll chunks (64 k-mers) request their 32-byte
 //           sectors before the first is consumed.  Lanes that share a minimizer share a line, so
 //           a warp-wide load touches ~5 lines instead of 32.
 //   FOLD    hits are rare; a ballot finds them and the warp folds them strictly in position order
