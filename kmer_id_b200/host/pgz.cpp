@@ -538,13 +538,14 @@ struct ParallelGunzip::Impl {
     uint64_t piece_end_bit(size_t k) const { return (uint64_t)std::min(size, (k + 1) * piece_bytes) * 8; }
     size_t max_out() const { return (size_t)kMaxExpand * piece_bytes + (1u << 20); }
 
-    void init_unknown_history(Run &r)
+    bool init_unknown_history(Run &r)
     {
-        r.sym.reserve(kWin + 6 * piece_bytes);
-        for (int i = 0; i < kWin; i++) r.sym.p[i] = (uint16_t)(256 + i);
         r.n = 0;
         r.ends.clear();
         r.eof = false;
+        if (!r.sym.reserve(kWin + 6 * piece_bytes)) return false; // out of memory: the piece is "not found"
+        for (int i = 0; i < kWin; i++) r.sym.p[i] = (uint16_t)(256 + i);
+        return true;
     }
 
     // speculative decode of piece k (k = 0 starts at the known first block)
@@ -553,7 +554,7 @@ struct ParallelGunzip::Impl {
         Piece &pc = pieces[k];
         const uint64_t stop_bit = piece_end_bit(k);
         if (k == 0) {
-            init_unknown_history(pc.run);
+            if (!init_unknown_history(pc.run)) { pc.found = false; return; }
             Bits in;
             in.seek(data, data + size, first_block_bit);
             pc.run.start_bit = first_block_bit;
@@ -565,7 +566,7 @@ struct ParallelGunzip::Impl {
             uint64_t cand, start;
             bool at_member;
             if (!find_block(data, size, from, stop_bit, cand, start, at_member)) break;
-            init_unknown_history(pc.run);
+            if (!init_unknown_history(pc.run)) break;
             Bits in;
             in.seek(data, data + size, start);
             pc.run.start_bit = start;
@@ -584,11 +585,11 @@ struct ParallelGunzip::Impl {
     {
         Piece &pc = pieces[k];
         Run &r = pc.run;
-        r.sym.reserve(kWin + 6 * piece_bytes);
-        for (int i = 0; i < kWin; i++) r.sym.p[i] = chain_window[i];
         r.n = 0;
         r.ends.clear();
         r.eof = false;
+        if (!r.sym.reserve(kWin + 6 * piece_bytes)) return false;
+        for (int i = 0; i < kWin; i++) r.sym.p[i] = chain_window[i];
         r.start_bit = chain_end_bit;
         Bits in;
         in.seek(data, data + size, chain_end_bit);
