@@ -12,6 +12,7 @@
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
 #include "device_warmup.hpp"
+#include "pgz.hpp"
 #include "read_reader.hpp"
 
 #include <chrono>
@@ -66,7 +67,9 @@ struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is 
 void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream *outread,
               std::vector<SavedRead> *saved)
 {
-    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes);
+    // R1 and R2 are inflated at the same time unless KID_SERIAL is set: share the cores
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, 3,
+                           default_gz_threads(getenv("KID_SERIAL") ? 1 : 2));
     std::vector<int32_t> taxon;
     std::vector<uint32_t> span;
     for (;;) {
@@ -90,7 +93,7 @@ void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::of
                         *outread << std::endl;
                         outread->write(bases, (std::streamsize)blen);
                         *outread << std::endl;
-                    } else {
+                    } else if (saved) {
                         SavedRead sr;
                         sr.taxon = fin;
                         sr.text = ">" + std::to_string(fin) + ":" + std::string(name, nlen) + "\n" +

@@ -22,10 +22,12 @@
 
 namespace kidhost {
 
-unsigned default_gz_threads()
+unsigned default_gz_threads(unsigned concurrent_files)
 {
     if (const char *e = getenv("KID_GZ_THREADS")) return (unsigned)std::max(0, atoi(e));
-    return std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    const unsigned h = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    if (h < 2) return 1; // zlib
+    return std::max(2u, concurrent_files > 1 ? h / concurrent_files : 3 * h / 4);
 }
 
 namespace {

@@ -56,8 +56,9 @@ void prewarm_batch_buffers(size_t max_bytes, int readers, bool with_quality, int
     for (void *p : got) pinned_put(p, bytes);
 }
 
-ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth)
-    : fmt_(fmt), max_reads_(max_reads), max_bytes_(max_bytes)
+ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth,
+                                 unsigned gz_threads)
+    : fmt_(fmt), max_reads_(max_reads), max_bytes_(max_bytes), gz_threads_(gz_threads)
 {
     const bool fastq = fmt == ReadFormat::GzFastq || fmt == ReadFormat::PlainFastq;
     for (int i = 0; i < depth; i++) {
@@ -165,7 +166,7 @@ void ReadBatchReader::run(std::string path)
 
 void ReadBatchReader::run_gz_fastq(const std::string &path)
 {
-    GzLineBlocks src(path);
+    GzLineBlocks src(path, 4u << 20, gz_threads_);
     LineBlock text;
     int mod4 = 0; // :768
     const char *seq = nullptr;
@@ -237,7 +238,7 @@ void ReadBatchReader::run_plain_fastq(const std::string &path)
 // kmer_read_m3.cpp:780-839 - gz lines; '>' lines start a record, other lines are concatenated
 void ReadBatchReader::run_gz_fasta(const std::string &path)
 {
-    GzLineBlocks src(path);
+    GzLineBlocks src(path, 4u << 20, gz_threads_);
     LineBlock text;
     std::string sequence, acc;
     auto lines = [&](const char *p, const char *end) {

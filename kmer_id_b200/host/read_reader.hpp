@@ -41,7 +41,9 @@ class ReadBatchReader {
 public:
     // starts a background thread that inflates/parses `path` into batches of at most max_reads
     // reads / max_bytes bases, keeping at most `depth` batches ahead of the consumer
-    ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth = 3);
+    // gz_threads: inflate workers for gz inputs (0 = default_gz_threads() of pgz.hpp)
+    ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth = 3,
+                    unsigned gz_threads = 0);
     ~ReadBatchReader();
     ReadBatch *next();          // blocks; the batch flagged `last` ends the stream
     void recycle(ReadBatch *b);
@@ -59,6 +61,7 @@ private:
 
     ReadFormat fmt_;
     size_t max_reads_, max_bytes_;
+    unsigned gz_threads_ = 0;
     std::vector<std::unique_ptr<ReadBatch>> pool_;
     std::deque<ReadBatch *> free_, ready_;
     std::mutex mu_;
