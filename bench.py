@@ -3,20 +3,24 @@
 
     python bench.py --gpus N --steps K --warmup W              (ours; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path)
+    python bench.py --config mito | x10                              (BASELINE.json configs[1] / [4])
 
-Workload (BASELINE.json configs[2], the largest single-GPU configuration): synthetic bact10-scale
-probe database (108 585 519 probes = sum of the shipped refkey10.txt counts, b10 taxonomy) and
-10 M synthetic 150-bp read pairs per GPU (tools/synth/kid_synth.h).  A *step* is one whole sample:
-kid_sample_begin -> classify every read of the batch -> sample end (ucount histogram, counts to
-the host; for N > 1 the cross-rank gcount sum / seen-bitmap OR).  A pair is two independently
-classified reads.
+Default workload (BASELINE.json configs[2], the largest single-GPU configuration): synthetic
+bact10-scale probe database (108 585 519 probes = sum of the shipped refkey10.txt counts, b10
+taxonomy) and 10 M synthetic 150-bp read pairs per GPU (tools/synth/kid_synth.h).  A *step* is one
+whole sample: kid_sample_begin -> classify every read of the batch -> sample end (ucount histogram,
+counts to the host; for N > 1 the cross-rank gcount sum / seen-bitmap OR).  A pair is two
+independently classified reads.
 
-  value  pairs/s with the batch already resident in HBM (CUDA events on the launching stream)
-  e2e    the same through kid_classify_host from pinned HOST buffers (H2D + D2H inside the region)
-  roofline.achieved = lookups/launch x 32 B / mean classify-kernel time  (32 B = one DRAM sector per
-           lookup); peak = MEASURED_PEAKS.json hbm_gbs
+  value  pairs/s with the TEXT batch (bases + qualities) already resident in HBM: kid_pack_kernel
+         (trim + 2-bit pack) + kid_classify3_kernel per step, CUDA events on the launching stream
+  e2e    pairs/s through kid_classify_packed_host from pinned HOST buffers holding the packed batch a
+         parser produces with kid_pack_reads (H2D + kernel + D2H inside the region); e2e_text is the
+         same through kid_classify_host from bases + qualities (what round 1 reported as e2e)
+  roofline.achieved = lookups/launch x 32 B / mean kid_classify3_kernel time (32 B = one DRAM sector
+         per lookup); peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline: the CPU oracle (a port, oracle/kid_oracle.c) single-threaded on a bounded sample;
-           its per-read taxa are compared with the GPU's for the same reads (parity_checked_reads)
+         its per-read taxa are compared with the GPU's for the same reads (parity_checked_reads)
   files_e2e    gz FASTQ files on disk -> _result.txt through kmer_id_b200/bin/nk10 (N = 1 only)
 
 Prints ONE JSON line on rank 0.
@@ -35,10 +39,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLDEN_B10 = os.path.join(ROOT, "tests", "golden", "b10")
+GOLDEN_MITO = os.path.join(ROOT, "tests", "golden", "mito")
 METRIC = "paired_reads_per_sec_classified"
 UNIT = "pairs/s"
-READ_LEN = 150
 SECTOR_BYTES = 32
+
+CONFIGS = {
+    "bact10": dict(label="BASELINE.json configs[2]: bact10-scale synthetic probe DB + 10M synthetic 150bp pairs per GPU",
+                   golden=GOLDEN_B10, tree="btree_10.txt", refkey="refkey10.txt", num=1, read_len=150,
+                   pairs=10_000_000, seeds=(10, 21), taxonomy="b10"),
+    "mito": dict(label="BASELINE.json configs[1]: mitochondria DB (kmer_read_m3 path) + 1M synthetic 150bp pairs per GPU",
+                 golden=GOLDEN_MITO, tree="mitochondria_tree.txt", refkey="mitochondria_refkey.txt", num=1,
+                 read_len=150, pairs=1_000_000, seeds=(11, 22), taxonomy="mitochondria"),
+    "x10": dict(label="BASELINE.json configs[4]: 10x bact10 synthetic probe DB + 4M synthetic 250bp pairs per GPU",
+                golden=GOLDEN_B10, tree="btree_10.txt", refkey="refkey10.txt", num=10, read_len=250,
+                pairs=4_000_000, seeds=(10, 25), taxonomy="b10"),
+}
 
 
 def parse_args():
@@ -47,8 +63,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU per step")
-    ap.add_argument("--db-den", type=int, default=1, help="probe DB = refkey counts / den")
+    ap.add_argument("--config", default="bact10", choices=sorted(CONFIGS))
+    ap.add_argument("--pairs", type=int, default=0, help="read pairs per GPU per step (0 = the config's)")
+    ap.add_argument("--db-den", type=int, default=1, help="probe DB = refkey counts x num / den")
     ap.add_argument("--cpu-baseline-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -58,21 +75,41 @@ def parse_args():
     ap.add_argument("--log2-sectors", type=int, default=0, help="table size override (0 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=80.0,
                     help="CPU seconds the reference arm may spend classifying (all steps together)")
-    return ap.parse_args()
+    ap.add_argument("--ref-den", type=int, default=1,
+                    help="reference arm: probe DB = refkey counts / den (1 = the benchmark's full DB; "
+                         "falls back to 100, and says so, when disk or RAM are short)")
+    a = ap.parse_args()
+    a.cfg = CONFIGS[a.config]
+    if a.pairs <= 0:
+        a.pairs = a.cfg["pairs"]
+    a.read_len = a.cfg["read_len"]
+    return a
 
 
-def workload_config(args, n_probes):
+def workload_config(args, n_probes, den=None, pairs=None):
+    den = args.db_den if den is None else den
+    pairs = args.pairs if pairs is None else pairs
+    L = args.read_len
     return {
-        "workload": "BASELINE.json configs[2]: bact10-scale synthetic probe DB + 10M synthetic 150bp pairs per GPU",
+        "workload": args.cfg["label"] + ("" if den == 1 else " - probe DB sampled 1/%d" % den),
         "db_probes": int(n_probes),
-        "db": "b10 taxonomy, refkey10 probe counts / %d, random canonical 30-mers (seed 10)" % args.db_den,
-        "pairs_per_gpu_per_step": args.pairs,
-        "read_len": READ_LEN,
-        "reads": "70% stitched from lineage probes, 0.5% subs, 0.1% N, 20% low-quality tails (seed 21)",
+        "db": "%s taxonomy, refkey probe counts x %d / %d, random canonical 30-mers (seed %d)"
+              % (args.cfg["taxonomy"], args.cfg["num"], den, args.cfg["seeds"][0]),
+        "pairs_per_gpu_per_step": int(pairs),
+        "read_len": L,
+        "reads": "70%% stitched from lineage probes, 0.5%% subs, 0.1%% N, 20%% low-quality tails (seed %d)" % args.cfg["seeds"][1],
         "sharding": "reads sharded across ranks, table replicated",
         "l2": "inputs_larger_than_l2 (%.1f GB of reads per step, GB-scale probe table: see table.bytes)"
-              % (args.pairs * 2 * READ_LEN * 2 / 1e9),
+              % (pairs * 2 * L * 2 / 1e9),
     }
+
+
+def make_workload(args, den=None):
+    from tools import synthlib
+    c = args.cfg
+    parent, prefix = synthlib.load_taxonomy(c["golden"], c["num"], args.db_den if den is None else den,
+                                            tree=c["tree"], refkey=c["refkey"])
+    return parent, synthlib.Workload(parent, prefix, read_len=c["read_len"], seed_db=c["seeds"][0], seed_reads=c["seeds"][1])
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -188,6 +225,24 @@ def bind_to_gpu_numa(local_rank: int):
 
 
 # ------------------------------------------------------------------------------------ ours
+def pack_on_host(kid, np, hseq, hqual, n_reads, read_len, hwords, hmeta):
+    """kid_pack_reads (the parser-side writer of packed batches) over the whole batch on ONE host
+    thread, slice by slice so that the words of consecutive slices follow each other; returns
+    (n_words, seconds).  Untimed setup: a parser does this while it still has each record in cache."""
+    step = 1 << 16
+    nw_total = 0
+    t0 = time.perf_counter()
+    seq, qual = hseq.numpy(), hqual.numpy()
+    words, meta = hwords.numpy().view(np.uint32), hmeta.numpy().view(np.uint32)
+    for r0 in range(0, n_reads, step):
+        n = min(step, n_reads - r0)
+        off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len))
+        w, _ = kid.pack_reads(seq[r0 * read_len:], qual[r0 * read_len:], off, word0=nw_total,
+                              words=words[nw_total:], meta=meta[2 * r0:])
+        nw_total += int(w.size)
+    return nw_total, time.perf_counter() - t0
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -195,7 +250,6 @@ def run_ours(args):
 
     import kmer_id_b200 as kid  # raises if the CUDA library is not built: no fallback
     from kmer_id_b200 import multi_gpu
-    from tools import synthlib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,12 +263,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
-    parent, prefix = synthlib.load_taxonomy(GOLDEN_B10, 1, args.db_den)
-    wl = synthlib.Workload(parent, prefix, read_len=READ_LEN)
+    READ_LEN = args.read_len
+    parent, wl = make_workload(args)
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- database: generated on the device, built by the library's own kernels
-    launches0 = kid.kernel_launches()
     dk = torch.empty(wl.n_probes, dtype=torch.int64, device=dev)
     dt = torch.empty(wl.n_probes, dtype=torch.int32, device=dev)
     wl.db_device(local, dk, dt, stream=stream)
@@ -225,8 +278,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     st = db.stats()
+    keep_keys = world == 1 and not args.no_cpu_baseline or world > 1 and rank == 0
+    hk = dk.cpu().numpy().view(np.uint64) if keep_keys else None  # the oracle checks below want the probe list
+    ht = dt.cpu().numpy().view(np.uint32) if keep_keys else None
+    del dk, dt
+    torch.cuda.empty_cache()
 
-    # ---- this rank's reads, resident in HBM
+    # ---- this rank's reads, resident in HBM as text (bases + qualities)
     n_reads = 2 * args.pairs
     nbytes = n_reads * READ_LEN
     dseq = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
@@ -238,17 +296,9 @@ def run_ours(args):
     engine, transport = multi_gpu.make_engine(sample, stream, prefer_peer=os.environ.get("KID_PEER", "1") != "0")
     torch.cuda.synchronize()
 
-    k_ev = []
-
-    def step_device(timed: bool):
+    def step_device():
         sample.begin(stream)
-        if timed:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
         sample.classify_device(dseq, dqual, doff, n_reads, dout, None, stream)
-        if timed:
-            b.record()
-            k_ev.append((a, b))
         return multi_gpu.finish(engine)
 
     def barrier():
@@ -257,7 +307,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        gcount, ucount = step_device(False)
+        gcount, ucount = step_device()
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -267,59 +317,122 @@ def run_ours(args):
     tc0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        gcount, ucount = step_device(True)
+        gcount, ucount = step_device()
     e1.record()
     barrier()
-    tc1 = time.perf_counter()
     gpu_launches = kid.kernel_launches() - l_before
     ms = e0.elapsed_time(e1)
     counters = sample.counters(stream)  # of the last step
-    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * args.pairs / (ms_per_step / 1e3)
-    if world == 1:
-        assert int(gcount.sum()) == counters["reads"], "gcount does not add up to the reads classified"
+    reads_kept = counters["reads"]
+    if world > 1:  # every read any rank kept is in the reduced gcount exactly once
+        t = torch.tensor([reads_kept], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        reads_kept = int(t.item())
+    assert int(gcount.astype(np.int64).sum()) == reads_kept, "gcount does not add up to the reads classified"
 
-    # ---- end to end through the host-buffer entry point
-    e2e = None
+    # ---- the dominant kernel alone: packed batch resident in HBM, CUDA events around each launch
+    cap = int(kid.lib.kid_pack_bound(n_reads, nbytes))
+    k_ms, pack_ms = [], []
+    if args.layout == "M":
+        dwords = torch.empty(cap, dtype=torch.int32, device=dev)
+        dmeta = torch.empty(2 * (n_reads + 1), dtype=torch.int32, device=dev)
+        for i in range(args.warmup + args.steps):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            sample.begin(stream)
+            a.record()
+            db.pack_device(dseq, dqual, doff, nbytes, n_reads, dwords, cap, dmeta, None, stream)
+            b.record()
+            sample.classify_packed_device(dwords, dmeta, n_reads, dout, stream)
+            c.record()
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                pack_ms.append(a.elapsed_time(b))
+                k_ms.append(b.elapsed_time(c))
+        g3, _ = sample.counts(stream)
+        if world == 1:
+            assert np.array_equal(g3, gcount), "packed-device path and text path disagree"
+        del dwords, dmeta
+    else:
+        for i in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sample.begin(stream)
+            a.record()
+            sample.classify_device(dseq, dqual, doff, n_reads, dout, None, stream)
+            b.record()
+            torch.cuda.synchronize()
+            k_ms.append(a.elapsed_time(b))
+    kernel_ms = statistics.mean(k_ms)
+    gpu_taxa = dout.cpu().numpy()
+
+    # ---- end to end through the host-buffer entry points
+    e2e = e2e_text = host_pack = None
     if not args.no_e2e:
         hseq = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
         hqual = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
         hseq.copy_(dseq)
         hqual.copy_(dqual)
-        hoff = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN))
         hout = torch.empty(n_reads, dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
 
-        def step_e2e():
+        def timed(fn):
+            hout.fill_(-7)
+            for _ in range(max(1, min(args.warmup, 2))):
+                g2, u2 = fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                g2, u2 = fn()
+            barrier()
+            dt_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt_s], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_s = float(t.item())
+            h2d, d2h = sample.transfer_bytes()
+            assert np.array_equal(g2, gcount) and np.array_equal(u2, ucount), "host and device paths disagree"
+            assert np.array_equal(hout.numpy(), gpu_taxa)
+            return {"value": world * args.pairs * args.steps / dt_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 8 * db.n_taxa),
+                    "ms_per_step": dt_s / args.steps * 1e3}
+
+        if args.layout == "M":
+            hwords = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+            hmeta = torch.empty(2 * (n_reads + 1), dtype=torch.int32, pin_memory=True)
+            n_words, pack_s = pack_on_host(kid, np, hseq, hqual, n_reads, READ_LEN, hwords, hmeta)
+            host_pack = {"reads_per_s_per_core": n_reads / pack_s, "text_GB_per_s_per_core": 2 * nbytes / pack_s / 1e9,
+                         "bytes_per_read": (4 * n_words + 8 * (n_reads + 1)) / n_reads,
+                         "what": "kid_pack_reads (process_qual trim + 2-bit pack) on one host thread, outside the timed region"}
+
+            def step_packed():
+                sample.begin(stream)
+                sample.classify_packed_host(hwords, hmeta, n_reads, hout)
+                return multi_gpu.finish(engine)
+
+            e2e = timed(step_packed)
+            e2e["input"] = "packed batch in pinned host memory (kid_pack_reads format), kid_classify_packed_host"
+
+        def step_text():
             sample.begin(stream)
             sample.classify_host(hseq, hqual, hoff, n_reads, hout, None)
             return multi_gpu.finish(engine)
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            g2, u2 = step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            g2, u2 = step_e2e()
-        barrier()
-        dt_e2e = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt_e2e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_e2e = float(t.item())
-        h2d, d2h = sample.transfer_bytes()
-        assert np.array_equal(g2, gcount) and np.array_equal(u2, ucount), "host and device paths disagree"
-        assert np.array_equal(hout.numpy(), dout.cpu().numpy())
-        e2e = {"value": world * args.pairs * args.steps / dt_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 8 * db.n_taxa),
-               "ms_per_step": dt_e2e / args.steps * 1e3}
+        hoff = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN))
+        e2e_text = timed(step_text)
+        e2e_text["input"] = "bases + qualities + offsets in pinned host memory, kid_classify_host"
+        if e2e is None:
+            e2e = e2e_text
     clk = clocks.stop(tc0, None)
 
+    # ---- N > 1: rank 0 checks its first reads against the CPU oracle (N = 1 does it in cpu_baseline)
+    parity_n = 0
+    if world > 1 and rank == 0:
+        parity_n = oracle_check(args, wl, hk, ht, parent, gpu_taxa, 100_000)
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -333,18 +446,25 @@ def run_ours(args):
     ceiling, ceiling_src = live_gather_ceiling(st["table_bytes"]) if world == 1 else (None, None)
     if ceiling is None:
         ceiling, ceiling_src = (tr or {}).get("gather_ceiling_gsectors_s"), "profiles/traffic.json"
-    roofline = {"bound": "hbm", "kernel": "kid_classify2_kernel" if args.layout == "M" else "kid_classify_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "kid_classify3_kernel" if args.layout == "M" else "kid_classify_kernel",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": (tr["dram_bytes_per_lookup"] * lookups if tr else None),
+                "traffic": (tr["dram_bytes_per_lookup"] * lookups if tr and args.config == "bact10" else None),
+                "traffic_source": (("constant: %.2f DRAM bytes per lookup (ncu dram__bytes_read+write of %s) x this run's lookups; "
+                                    "not re-measured in this run") % (tr["dram_bytes_per_lookup"], tr.get("source", "profiles/traffic.json"))
+                                   if tr and args.config == "bact10" else None),
                 "algorithmic_bytes_per_lookup": SECTOR_BYTES, "lookups_per_launch": lookups,
                 "kernel_ms": kernel_ms, "lookups_per_s": lookups / (kernel_ms / 1e3),
+                "pack_kernel_ms": statistics.mean(pack_ms) if pack_ms else None,
+                "pack_kernel_text_GB_per_s": (2 * nbytes / (statistics.mean(pack_ms) / 1e3) / 1e9 if pack_ms else None),
                 "random_sector_gather_ceiling_gsectors_s": ceiling, "gather_ceiling_source": ceiling_src}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
-        "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e,
+        "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e, "e2e_text": e2e_text,
+        "host_pack": host_pack,
         "gpu_launches": int(gpu_launches), "roofline": roofline,
         "lookups_per_s_whole_step": world * lookups / (ms_per_step / 1e3),
         "table": {"layout": args.layout, "bytes": st["table_bytes"], "distinct_keys": st["n_distinct"], "displaced": st["n_displaced"],
@@ -355,13 +475,15 @@ def run_ours(args):
         "numa_node_rank0": numa,
         "hit_fraction": counters["hits"] / max(1, lookups),
         "classified_fraction": float((gcount[2:].sum()) / max(1, gcount.sum())),
+        "reads_kept_all_ranks": int(reads_kept),
     }
+    if parity_n:
+        out["parity_checked_reads"] = parity_n
 
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_port(args, wl, dk, dt, parent, dout.cpu().numpy())
-    if world == 1 and not args.no_files_e2e:
+        out["cpu_baseline"] = cpu_baseline_port(args, wl, hk, ht, parent, gpu_taxa)
+    if world == 1 and not args.no_files_e2e and args.config == "bact10":
         out["files_e2e"] = files_e2e(args)
-    del dk, dt
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -386,7 +508,8 @@ def files_e2e(args):
         fq = os.path.join(work, "fq")
         subprocess.run([synth, "db", "--golden", GOLDEN_B10, "--out", work, "--den", str(args.db_den)], check=True,
                        stdout=subprocess.DEVNULL)
-        for i in range(3):
+        n_samples = 5
+        for i in range(n_samples):
             subprocess.run([synth, "reads", "--golden", GOLDEN_B10, "--out", fq, "--sample", "s%d" % i, "--pairs",
                             str(pairs), "--first-pair", str(i * pairs), "--den", str(args.db_den)], check=True,
                            stdout=subprocess.DEVNULL)
@@ -398,26 +521,26 @@ def files_e2e(args):
             return {"error": "nk10 exited %d: %s" % (r.returncode, r.stderr[-300:])}
         per_sample = [float(x) for x in re.findall(r"\[nk10\] s\d+: \d+ reads, \d+ lookups, \d+ hits in ([0-9.]+) s", r.stderr)]
         m = re.search(r"\[nk10\] parse db ([0-9.]+) s, build table ([0-9.]+) s, total ([0-9.]+) s", r.stderr)
-        best = min(per_sample)
-        return {"value": pairs / best, "unit": UNIT,
-                "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, fastest of 3 samples "
-                        "(R1 and R2 inflated on all host cores, parsed, classified); probe DB parsed from gz text",
-                "pairs_per_sample": pairs, "sample_s": per_sample, "db_parse_s": float(m.group(1)),
+        med = statistics.median(per_sample)
+        return {"value": pairs / med, "unit": UNIT,
+                "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, MEDIAN of %d samples in one "
+                        "process (inflate on all host cores, parse + trim + pack, classify); probe DB parsed from gz text"
+                        % n_samples,
+                "pairs_per_sample": pairs, "sample_s": per_sample,
+                "first_sample_pairs_per_s": pairs / per_sample[0], "best_sample_pairs_per_s": pairs / min(per_sample),
+                "db_parse_s": float(m.group(1)),
                 "table_build_s": float(m.group(2)), "process_total_s": float(m.group(3)), "wall_s": wall,
-                "whole_run_pairs_per_s": 3 * pairs / wall, "host_cores": os.cpu_count()}
+                "whole_run_pairs_per_s": n_samples * pairs / wall, "host_cores": os.cpu_count()}
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
 
-def cpu_baseline_port(args, wl, dk, dt, parent, gpu_taxa):
-    """The CPU oracle (kind = "port"), one thread, on the first cpu_baseline_reads reads of the same
-    workload against the FULL probe table (so its cache behaviour is the real one).  Its per-read
-    taxa double as a parity check of what the timed GPU steps computed for those reads."""
+def oracle_check(args, wl, keys, taxa, parent, gpu_taxa, n, timing=None):
+    """first n reads of rank 0's batch through the CPU oracle over the FULL probe table; aborts the
+    bench on the first read whose taxon differs from what the timed GPU steps produced"""
     import numpy as np
     from oracle import kor
-    n = min(args.cpu_baseline_reads, 2 * args.pairs)
-    keys = dk.cpu().numpy().view(np.uint64)
-    taxa = dt.cpu().numpy().view(np.uint32)
+    n = min(n, gpu_taxa.size)
     odb = kor.OracleDB(wl.n_taxa)
     odb.set_parents(parent)
     odb.add_keys(keys, taxa)
@@ -431,48 +554,79 @@ def cpu_baseline_port(args, wl, dk, dt, parent, gpu_taxa):
         bad = int(np.flatnonzero(fin != gpu_taxa[:n])[0])
         raise SystemExit("bench.py: GPU and oracle disagree on read %d of the benchmark batch: %d vs %d"
                          % (bad, int(gpu_taxa[bad]), int(fin[bad])))
-    return {"value": (n / 2) / dt_s, "unit": UNIT, "cores": 1, "kind": "port", "parity_checked_reads": int(n),
+    if timing is not None:
+        timing.update(seconds=dt_s, lookups=osamp.lookups)
+    return int(n)
+
+
+def cpu_baseline_port(args, wl, keys, taxa, parent, gpu_taxa):
+    """The CPU oracle (kind = "port"), one thread, on the first cpu_baseline_reads reads of the same
+    workload against the FULL probe table (so its cache behaviour is the real one).  Its per-read
+    taxa double as a parity check of what the timed GPU steps computed for those reads."""
+    tm = {}
+    n = oracle_check(args, wl, keys, taxa, parent, gpu_taxa, min(args.cpu_baseline_reads, 2 * args.pairs), tm)
+    return {"value": (n / 2) / tm["seconds"], "unit": UNIT, "cores": 1, "kind": "port", "parity_checked_reads": int(n),
             "sample": "first %d reads of rank 0's batch, full %d-probe table, oracle/kid_oracle.c" % (n, keys.size),
-            "lookups_per_s": osamp.lookups / dt_s, "seconds": dt_s}
+            "lookups_per_s": tm["lookups"] / tm["seconds"], "seconds": tm["seconds"]}
 
 
 # ------------------------------------------------------------------------------------ reference
 def run_reference(args):
     """The reference's own CPU implementation: oracle/_ref/nk10 (unmodified newkmer_10nx.cpp,
-    single-threaded - it has no threading) on a bounded sample of the workload: a 1/100-scale probe
-    DB in its own text format and (warmup+steps) samples of P pairs each, one nk10 process; a step is
-    one sample, timed from its name line to its second "reads loaded" line on stdout."""
+    single-threaded - it has no threading) on the benchmark's probe DB in its own text format and
+    (warmup+steps) samples of P pairs each, one nk10 process; a step is one sample, timed from its
+    name line to its second "reads loaded" line on stdout.  P is bounded by --ref-seconds; the
+    `config` printed is the one actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import shutil
     import tempfile
     nk10 = os.path.join(ROOT, "oracle", "_ref", "nk10")
     synth = os.path.join(ROOT, "tools", "kid_synth")
     n_samples = args.warmup + args.steps
-    if not (os.path.exists(nk10) and os.path.exists(synth)):
+    if args.config != "bact10" or not (os.path.exists(nk10) and os.path.exists(synth)):
+        # mito: the m3 reader's CLI differs; x10: the reference cannot load it (newkmer_10nx.cpp:256-260)
         return run_reference_port(args)
     pairs = max(2000, int(args.ref_seconds * 16000 / max(1, n_samples)))  # ~32 k reads/s single thread
-    den = 100
+    den = args.ref_den
+    note = ""
+    if den == 1:
+        free_disk = shutil.disk_usage(tempfile.gettempdir()).free
+        try:
+            avail_ram = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
+        except Exception:
+            avail_ram = 0
+        if free_disk < 6 << 30 or avail_ram < 40 << 30:
+            den, note = 100, " (full DB needs 6 GB of disk and 40 GB of RAM: %.0f / %.0f GB free)" % (free_disk / 2**30, avail_ram / 2**30)
     work = tempfile.mkdtemp(prefix="kid_ref_")
     fq = os.path.join(work, "fq")
+    t_gen = time.perf_counter()
     subprocess.run([synth, "db", "--golden", GOLDEN_B10, "--out", work, "--den", str(den)], check=True,
                    stdout=subprocess.DEVNULL)
     for i in range(n_samples):
         subprocess.run([synth, "reads", "--golden", GOLDEN_B10, "--out", fq, "--sample", "s%03d" % i,
                         "--pairs", str(pairs), "--first-pair", str(i * pairs), "--den", str(den)], check=True,
                        stdout=subprocess.DEVNULL)
+    t_gen = time.perf_counter() - t_gen
+    t_start = time.perf_counter()
     proc = subprocess.Popen([nk10, fq + "/"], cwd=work, stdout=subprocess.PIPE, text=True)
     stamps = []
     for line in proc.stdout:
         stamps.append((time.perf_counter(), line.rstrip("\n")))
     proc.wait()
+    shutil.rmtree(work, ignore_errors=True)
     if proc.returncode != 0:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/nk10 exited %d" % proc.returncode}))
         return
     steps = []
+    n_probes = None
+    load_s = None
     i = 0
     while i < len(stamps):
         t, text = stamps[i]
+        if text.endswith(" kmers loaded"):
+            n_probes, load_s = int(text.split()[0]), t - t_start
         if text.startswith("s") and len(text) == 4 and text[1:].isdigit():
             # name line, "<n> reads loaded", "<n> reads loaded"
             t_end, last = stamps[i + 2]
@@ -483,34 +637,33 @@ def run_reference(args):
     timed = steps[args.warmup:] if len(steps) > args.warmup else steps
     sec = statistics.mean(s for s, _ in timed)
     value = pairs / sec
-    import shutil
-    shutil.rmtree(work, ignore_errors=True)
-    cfg = workload_config(args, 108_585_519)
+    cfg = workload_config(args, n_probes, den=den, pairs=pairs)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
            "config": cfg,
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                            "sample": "unmodified nk10 (g++ -O3), 1 thread; probe DB sampled 1/%d (%s lines of text) in "
-                                      "its 2^30-cell table, %d pairs per step, %d steps in one process"
-                                      % (den, "1083547", pairs, n_samples)},
+                            "sample": "unmodified nk10 (g++ -O3), 1 thread (it has no threading); probe DB = refkey counts / %d "
+                                      "(%d lines of text)%s in its 2^30-cell table, %d pairs per step (the GPU arm: %d), "
+                                      "%d steps in one process; DB load %.0f s and input generation %.0f s are outside the steps"
+                                      % (den, n_probes, note, pairs, args.pairs, n_samples, load_s or 0, t_gen)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
 def run_reference_port(args):
-    """Fallback when oracle/_ref/nk10 is absent: the in-repo CPU port, one thread."""
+    """The in-repo CPU port (oracle/kid_oracle.c), one thread: when oracle/_ref/nk10 is absent, and for
+    the configs the reference binary cannot run from this command line (mito, x10)."""
     import numpy as np
     from oracle import kor
-    from tools import synthlib
-    parent, prefix = synthlib.load_taxonomy(GOLDEN_B10, 1, 100)
-    wl = synthlib.Workload(parent, prefix, read_len=READ_LEN)
+    den = args.ref_den if args.config != "x10" else max(args.ref_den, 10)  # 1.09 G keys: 35 GB of host RAM
+    parent, wl = make_workload(args, den=den)
     keys, taxa = wl.db_host()
     odb = kor.OracleDB(wl.n_taxa)
     odb.set_parents(parent)
     odb.add_keys(keys, taxa)
     n_samples = args.warmup + args.steps
-    pairs = max(2000, int(args.ref_seconds * 30000 / max(1, n_samples)))
+    pairs = max(2000, int(args.ref_seconds * 30000 * 150 / args.read_len / max(1, n_samples)))
     osamp = kor.OracleSample(odb)
     secs = []
     for i in range(n_samples):
@@ -525,9 +678,10 @@ def run_reference_port(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
-           "config": workload_config(args, 108_585_519),
+           "config": workload_config(args, wl.n_probes, den=den, pairs=pairs),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": "oracle/kid_oracle.c, 1/100 probe DB, %d pairs per step" % pairs},
+                            "sample": "oracle/kid_oracle.c, probe DB = refkey counts x %d / %d (%d keys), %d pairs per step (the GPU arm: %d)"
+                                      % (args.cfg["num"], den, keys.size, pairs, args.pairs)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

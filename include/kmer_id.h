@@ -105,7 +105,8 @@ int kid_sample_begin(kid_sample *s, void *stream); /* zero gcount/seen/counters,
  * getHash/msca for a whole batch, ON THE GIVEN STREAM, with every buffer already on the device.
  *   seq, qual   device byte buffers; read r occupies [off[r], off[r+1]) in both (same offsets).
  *               qual == NULL: no trimming, reads need length > 30 (process_fagz :849-852).
- *               Both buffers must be readable for 16 bytes past off[n_reads] (padding).
+ *               Both buffers must be readable for 16 bytes past off[n_reads] (padding) and seq
+ *               must be 16-byte aligned (the kernel loads aligned 128-bit words; KID_EINVAL otherwise).
  *   off         device uint64[n_reads+1]
  *   out_taxon   device int32[n_reads] or NULL: final_targ (:616), or -1 if the read was dropped
  *               by the length rule (:755) and therefore not counted anywhere.
@@ -126,6 +127,73 @@ int kid_classify_host(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
 int kid_sample_set_chunk_reads(kid_sample *s, size_t chunk_reads);
 /* bytes moved by kid_classify_host since kid_sample_begin (for bench.py's e2e accounting) */
 int kid_sample_transfer_bytes(const kid_sample *s, uint64_t *h2d, uint64_t *d2h);
+
+/* ---- packed read batches ----------------------------------------------------------------------
+ * What the k-mer scan actually consumes, and what a host parser should ship instead of text: per read
+ * only the bases that survive process_qual's trim (:714-760), as 2-bit codes.  150-base reads cost
+ * 48 bytes each on the wire instead of 308 (bases + qualities + offset), and qualities never leave
+ * the host.
+ *   words   uint32 stream.  A read's trimmed bases seq[start..stop], 16 per word, first base in the
+ *           top bit pair, A/a 0, C/c 1, G/g 2, T/t 3 (U/u 3 with KID_DB_ACCEPT_U), any other byte 0;
+ *           the last word zero padded.  If (and only if) the read has KID_PK_INVALID set,
+ *           ceil(tlen/32) validity words follow its code words: first base in the top bit,
+ *           1 = the byte was one of the accepted letters (:480-524), zero padded.
+ *   meta    uint32[2*(n_reads+1)]: meta[2r] = index of the read's first word | KID_PK_INVALID,
+ *           meta[2r+1] = tlen = stop-start+1, or 0 for a read the length rule drops
+ *           (stop-start < 30, :755 - such a read needs no words).  Entry n_reads = {end index, 0}.
+ *           Word indices are non-decreasing and below 2^31; gaps between reads are allowed.
+ * kid_pack_reads writes this format on the host (the trim is process_qual's, on the calling thread,
+ * the packing is SIMD); kid_classify_device / kid_classify_host write it on the device with
+ * kid_pack_kernel when they are given text. */
+#define KID_PK_INVALID 0x80000000u
+#define KID_PACK_IMPL_BYTES 0x100u /* kid_pack_reads: force the byte-loop packer (the format's definition) */
+#define KID_PACK_IMPL_SWAR 0x200u  /* ... the 64-bit SWAR packer instead of AVX2 */
+/* words that n_reads reads totalling `bases` bases can need at most */
+size_t kid_pack_bound(size_t n_reads, uint64_t bases);
+/* Host-side packer: replaces process_qual (:714-760) and the base switch of process_read
+ * (:477-525) for reads [0, n_reads) of a text batch laid out as for kid_classify_host.
+ *   flags      KID_DB_ACCEPT_U or 0 (| KID_PACK_IMPL_* in tests: all implementations agree)
+ *   word0      index the first word written gets in meta (the caller appends batch after batch)
+ *   words      receives the words; words_cap entries available (see kid_pack_bound)
+ *   meta       2*(n_reads+1) entries
+ *   span       2*n_reads entries or NULL: (start, stop) as process_qual leaves them
+ *   n_words    out: words written
+ * Reads and writes host memory only; thread safe. */
+int kid_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *off, size_t n_reads,
+                   unsigned flags, uint32_t word0, uint32_t *words, size_t words_cap, uint32_t *meta,
+                   uint32_t *span, size_t *n_words);
+/* Device-side packer (kid_pack_kernel): the same conversion for a text batch that is already on the
+ * device (buffers as for kid_classify_device, off[0] = 0, total_bases = off[n_reads]).  Read r's words
+ * start at off[r]/16 + off[r]/32 + 2r, so words_cap must be at least kid_pack_bound(n_reads,
+ * total_bases); the gaps are never read.  Long reads (> 496 bases) always carry validity words.
+ * Asynchronous on `stream`. */
+int kid_pack_device(const kid_db *db, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                    uint64_t total_bases, size_t n_reads, uint32_t *words, size_t words_cap,
+                    uint32_t *meta, uint32_t *out_span, void *stream);
+/* kid_classify_packed_device: process_read (:452-617) + getHash/msca for a packed batch whose words
+ * and meta are ALREADY on the device, on the given stream.  meta[].x word indices are relative to
+ * `words`.  out_taxon: device int32[n_reads] or NULL, -1 for dropped reads.  Asynchronous. */
+int kid_classify_packed_device(kid_sample *s, const uint32_t *words, const uint32_t *meta,
+                               size_t n_reads, int32_t *out_taxon, void *stream);
+/* kid_classify_packed_host: same from HOST buffers, chunked and double-buffered like
+ * kid_classify_host; returns when out_taxon (host int32[n_reads] or NULL) is complete.  words[0] is
+ * the word with index word0 (= the word0 given to kid_pack_reads). */
+int kid_classify_packed_host(kid_sample *s, const uint32_t *words, uint32_t word0, const uint32_t *meta,
+                             size_t n_reads, int32_t *out_taxon);
+
+/* ---- asynchronous slots -------------------------------------------------------------------------
+ * One host thread pipelines parse | H2D | kernels | D2H: it fills a pinned buffer, submits it on a
+ * slot and goes on parsing; kid_wait(slot) returns when that slot's outputs are complete and its
+ * input buffers may be reused.  A slot is one CUDA stream plus device staging buffers owned by the
+ * sample; submissions on one slot run in order, different slots overlap.  The caller owns the host
+ * buffers (kid_host_alloc) and must not touch them between submit and kid_wait.  Replaces the
+ * synchronous per-record call at newkmer_10nx.cpp:798-801. */
+#define KID_MAX_SLOTS 4
+int kid_classify_async(kid_sample *s, int slot, const uint8_t *seq, const uint8_t *qual,
+                       const uint64_t *off, size_t n_reads, int32_t *out_taxon, uint32_t *out_span);
+int kid_classify_packed_async(kid_sample *s, int slot, const uint32_t *words, uint32_t word0,
+                              const uint32_t *meta, size_t n_reads, int32_t *out_taxon);
+int kid_wait(kid_sample *s, int slot);
 
 /* ---- sample end -------------------------------------------------------------------------------
  * kid_sample_counts: replaces the read-out loop main():1040-1043.  Computes ucount as the

@@ -53,6 +53,14 @@ _SIGS = {
     "kid_sample_begin": (_i, [_vp, _vp]),
     "kid_classify_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "kid_classify_host": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "kid_pack_bound": (_sz, [_sz, _u64]),
+    "kid_pack_reads": (_i, [_vp, _vp, _vp, _sz, _u, C.c_uint32, _vp, _sz, _vp, _vp, C.POINTER(_sz)]),
+    "kid_pack_device": (_i, [_vp, _vp, _vp, _vp, _u64, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "kid_classify_packed_device": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "kid_classify_packed_host": (_i, [_vp, _vp, C.c_uint32, _vp, _sz, _vp]),
+    "kid_classify_async": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "kid_classify_packed_async": (_i, [_vp, _i, _vp, C.c_uint32, _vp, _sz, _vp]),
+    "kid_wait": (_i, [_vp, _i]),
     "kid_sample_set_chunk_reads": (_i, [_vp, _sz]),
     "kid_sample_transfer_bytes": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "kid_sample_counts": (_i, [_vp, _vp, _vp, _vp]),
@@ -72,6 +80,10 @@ for _name, (_res, _args) in _SIGS.items():
 
 KID_DB_ACCEPT_U = 1
 KID_DB_LAYOUT_KEYHASH = 2
+KID_PK_INVALID = 0x80000000
+KID_PACK_IMPL_BYTES = 0x100
+KID_PACK_IMPL_SWAR = 0x200
+KID_MAX_SLOTS = 4
 ERROR_NAMES = {-1: "KID_EINVAL", -2: "KID_ECUDA", -3: "KID_ENOMEM", -4: "KID_ERANGE",
                -5: "KID_ETREE", -6: "KID_EFULL"}
 
@@ -113,6 +125,31 @@ def _as_ptr(x) -> Optional[int]:
     return x.data_ptr()  # torch.Tensor
 
 
+def pack_reads(seq: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray, flags: int = 0,
+               word0: int = 0, want_span: bool = False, words: Optional[np.ndarray] = None,
+               meta: Optional[np.ndarray] = None):
+    """kid_pack_reads on numpy arrays (host only, no GPU needed): text batch -> (words, meta[, span]).
+    `words` / `meta` may be preallocated (e.g. views of pinned memory); words is returned cut to size."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = off.size - 1
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    cap = int(lib.kid_pack_bound(n, int(off[-1] - off[0])))
+    if words is None:
+        words = np.empty(cap, dtype=np.uint32)
+    if meta is None:
+        meta = np.empty(2 * (n + 1), dtype=np.uint32)
+    assert meta.size >= 2 * (n + 1) and words.dtype == np.uint32 and meta.dtype == np.uint32
+    span = np.zeros((n, 2), dtype=np.uint32) if want_span else None
+    nw = _sz(0)
+    _check(lib.kid_pack_reads(_np_ptr(seq), _np_ptr(qual) if qual is not None else None, _np_ptr(off), n, flags,
+                              word0, _np_ptr(words), words.size, _np_ptr(meta),
+                              _np_ptr(span) if span is not None else None, C.byref(nw)))
+    out = (words[:nw.value], meta[:2 * (n + 1)])
+    return out + (span,) if want_span else out
+
+
 class Database:
     """GPU-resident probe table + taxonomy (Hashtable + Tree1 of the reference)."""
 
@@ -147,6 +184,12 @@ class Database:
         _check(lib.kid_db_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"n_distinct": a.value, "n_sectors": b.value, "table_bytes": c.value,
                 "n_displaced": d.value}
+
+    def pack_device(self, seq, qual, off, total_bases: int, n_reads: int, words, words_cap: int, meta,
+                    out_span=None, stream: int = 0):
+        """kid_pack_device: text batch on the device -> packed batch on the device (raw addresses / tensors)."""
+        _check(lib.kid_pack_device(self._h, _as_ptr(seq), _as_ptr(qual), _as_ptr(off), total_bases, n_reads,
+                                   _as_ptr(words), words_cap, _as_ptr(meta), _as_ptr(out_span), stream or None))
 
     def table_device(self) -> Tuple[int, int]:
         p, n = _vp(), _u64()
@@ -198,6 +241,27 @@ class Sample:
         """Host buffers (numpy arrays or pinned torch tensors); returns when outputs are complete."""
         _check(lib.kid_classify_host(self._h, _as_ptr(seq), _as_ptr(qual), _as_ptr(off), n_reads,
                                      _as_ptr(out_taxon), _as_ptr(out_span)))
+
+    def classify_packed_device(self, words, meta, n_reads: int, out_taxon=None, stream: int = 0):
+        """Packed batch already on the device (torch tensors or raw addresses)."""
+        _check(lib.kid_classify_packed_device(self._h, _as_ptr(words), _as_ptr(meta), n_reads,
+                                              _as_ptr(out_taxon), stream or None))
+
+    def classify_packed_host(self, words, meta, n_reads: int, out_taxon=None, word0: int = 0):
+        """Packed batch in host memory; returns when out_taxon is complete."""
+        _check(lib.kid_classify_packed_host(self._h, _as_ptr(words), word0, _as_ptr(meta), n_reads,
+                                            _as_ptr(out_taxon)))
+
+    def classify_async(self, slot: int, seq, qual, off, n_reads: int, out_taxon=None, out_span=None):
+        _check(lib.kid_classify_async(self._h, slot, _as_ptr(seq), _as_ptr(qual), _as_ptr(off), n_reads,
+                                      _as_ptr(out_taxon), _as_ptr(out_span)))
+
+    def classify_packed_async(self, slot: int, words, meta, n_reads: int, out_taxon=None, word0: int = 0):
+        _check(lib.kid_classify_packed_async(self._h, slot, _as_ptr(words), word0, _as_ptr(meta), n_reads,
+                                             _as_ptr(out_taxon)))
+
+    def wait(self, slot: int):
+        _check(lib.kid_wait(self._h, slot))
 
     def classify(self, seq: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray,
                  want_span: bool = False):

@@ -51,13 +51,16 @@ struct DeviceGuard { // make `device` current for the call, restore the caller's
     }
 };
 
-struct HostSlot { // one half of kid_classify_host's double buffer
+struct HostSlot { // one asynchronous slot: a stream and its device staging buffers
     cudaStream_t stream = nullptr;
-    uint8_t *seq = nullptr, *qual = nullptr;
+    uint8_t *seq = nullptr, *qual = nullptr; // text batches
     uint64_t *off = nullptr;
+    uint32_t *words = nullptr;               // packed batch: copied from the host or written by kid_pack_kernel
+    uint2 *meta = nullptr;
     int32_t *out_taxon = nullptr;
     uint32_t *out_span = nullptr;
-    size_t cap_bytes = 0, cap_reads = 0;
+    size_t cap_bytes = 0, cap_reads = 0, cap_words = 0;
+    bool has_qual = false;
 };
 
 } // namespace
@@ -93,7 +96,8 @@ struct kid_sample {
     uint64_t n_words = 0;
     unsigned long long *counters = nullptr;
     cudaEvent_t begin_ev = nullptr;
-    HostSlot slot[2];
+    HostSlot slot[KID_MAX_SLOTS];
+    HostSlot dev; // scratch of kid_classify_device (packed form of a text batch); no stream of its own
     size_t chunk_reads = (size_t)1 << 18;
     uint64_t h2d = 0, d2h = 0;
 };
@@ -453,7 +457,9 @@ void kid_sample_free(kid_sample *s)
     for (HostSlot &h : s->slot) {
         if (h.stream) { cudaStreamSynchronize(h.stream); cudaStreamDestroy(h.stream); }
         cudaFree(h.seq); cudaFree(h.qual); cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
+        cudaFree(h.words); cudaFree(h.meta);
     }
+    cudaFree(s->dev.words); cudaFree(s->dev.meta);
     if (s->begin_ev) cudaEventDestroy(s->begin_ev);
     cudaFree(s->gcount); cudaFree(s->ucount); cudaFree(s->own_seen); cudaFree(s->counters);
     delete s;
@@ -500,15 +506,164 @@ static KidClassifyParams make_params(kid_sample *s, const uint8_t *seq, const ui
     return p;
 }
 
+static KidPackedParams make_packed_params(kid_sample *s, const uint32_t *words, const uint2 *meta, uint32_t bias,
+                                           size_t n, int32_t *out_taxon)
+{
+    KidPackedParams p;
+    p.table2 = s->db->table_view2();
+    p.tree = s->db->tree_view();
+    p.words = words;
+    p.meta = meta;
+    p.word_bias = bias;
+    p.n_reads = n;
+    p.out_taxon = out_taxon;
+    p.gcount = s->gcount;
+    p.seen = s->seen;
+    p.counters = s->counters;
+    return p;
+}
+
+// the fused text kernels: layout K (bake-off only) and, on request, the round-1 layout M kernel
+static bool use_fused_text_kernel(const kid_db *db)
+{
+    static const bool forced = getenv("KID_FUSED_TEXT_KERNEL") != nullptr;
+    return db->layout == KID_LAYOUT_KEYHASH || forced;
+}
+
+static int reserve_packed(HostSlot &h, size_t words, size_t reads)
+{
+    if (words + 16 > h.cap_words) {
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.words);
+        h.words = nullptr;
+        h.cap_words = 0;
+        const size_t cap = words + words / 4 + 16;
+        KID_CUDA(cudaMalloc(&h.words, sizeof(uint32_t) * cap));
+        h.cap_words = cap;
+    }
+    if (reads > h.cap_reads || !h.meta) {
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span); cudaFree(h.meta);
+        h.off = nullptr; h.out_taxon = nullptr; h.out_span = nullptr; h.meta = nullptr;
+        h.cap_reads = 0;
+        const size_t cap = reads + reads / 4 + 16;
+        KID_CUDA(cudaMalloc(&h.off, sizeof(uint64_t) * (cap + 1)));
+        KID_CUDA(cudaMalloc(&h.meta, sizeof(uint2) * (cap + 1)));
+        KID_CUDA(cudaMalloc(&h.out_taxon, sizeof(int32_t) * cap));
+        KID_CUDA(cudaMalloc(&h.out_span, sizeof(uint32_t) * 2 * cap));
+        h.cap_reads = cap;
+    }
+    return KID_OK;
+}
+
+static int reserve_text(HostSlot &h, size_t bytes, bool want_qual)
+{
+    if (bytes + 64 > h.cap_bytes || (want_qual && !h.has_qual)) {
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.seq); cudaFree(h.qual);
+        h.seq = h.qual = nullptr;
+        size_t cap = bytes + bytes / 4 + 64;
+        if (cap < h.cap_bytes) cap = h.cap_bytes;
+        h.cap_bytes = 0;
+        h.has_qual = false;
+        KID_CUDA(cudaMalloc(&h.seq, cap));
+        if (want_qual) KID_CUDA(cudaMalloc(&h.qual, cap));
+        h.has_qual = want_qual;
+        h.cap_bytes = cap;
+    }
+    return KID_OK;
+}
+
+// text on the device -> packed form in h.words/h.meta -> k-mer scan, all on `stream`
+static int pack_and_scan(kid_sample *s, HostSlot &h, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                         uint64_t bias, uint64_t bytes, size_t n, int32_t *out_taxon, uint32_t *out_span,
+                         cudaStream_t stream)
+{
+    const uint64_t bound = kid_pack_word_index(bytes, n) + 2;
+    if (bound >= 0x80000000ull)
+        return fail(KID_ERANGE, "a text batch of %llu bases in %zu reads needs more than 2^31 packed words; split it",
+                    (unsigned long long)bytes, n);
+    int rc = reserve_packed(h, (size_t)bound, n);
+    if (rc) return rc;
+    KidPackParams pp;
+    pp.seq = seq;
+    pp.qual = qual;
+    pp.off = off;
+    pp.off_bias = bias;
+    pp.n_reads = n;
+    pp.words = h.words;
+    pp.meta = h.meta;
+    pp.out_span = out_span;
+    pp.accept_u = (s->db->flags & KID_DB_ACCEPT_U) != 0;
+    KID_CUDA(kid_launch_pack(pp, s->db->sm_count, stream));
+    KidPackedParams p = make_packed_params(s, h.words, h.meta, 0, n, out_taxon);
+    KID_CUDA(kid_launch_classify3(p, s->db->sm_count, stream));
+    return KID_OK;
+}
+
 int kid_classify_device(kid_sample *s, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
-                        size_t n_reads, int32_t *out_taxon, uint32_t *out_span, void *stream)
+                        size_t n_reads, int32_t *out_taxon, uint32_t *out_span, void *stream_)
 {
     if (!s) return fail(KID_EINVAL, "kid_classify_device: s is NULL");
     if (n_reads == 0) return KID_OK;
     if (!seq || !off) return fail(KID_EINVAL, "kid_classify_device: seq/off is NULL");
+    if (reinterpret_cast<uintptr_t>(seq) & 15)
+        return fail(KID_EINVAL, "kid_classify_device: seq must be 16-byte aligned (the kernels load aligned 128-bit words)");
     DeviceGuard guard(s->db->device);
-    KidClassifyParams p = make_params(s, seq, qual, off, 0, n_reads, out_taxon, out_span);
-    KID_CUDA(launch_classify(s->db, p, (cudaStream_t)stream));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (use_fused_text_kernel(s->db)) {
+        KidClassifyParams p = make_params(s, seq, qual, off, 0, n_reads, out_taxon, out_span);
+        KID_CUDA(launch_classify(s->db, p, stream));
+        return KID_OK;
+    }
+    // the packed form's size depends on the batch's bases: two offsets come back to the host
+    uint64_t ends[2] = { 0, 0 };
+    KID_CUDA(cudaMemcpyAsync(&ends[0], off, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    KID_CUDA(cudaMemcpyAsync(&ends[1], off + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    KID_CUDA(cudaStreamSynchronize(stream));
+    if (ends[0] != 0) return fail(KID_EINVAL, "kid_classify_device: off[0] must be 0");
+    return pack_and_scan(s, s->dev, seq, qual, off, 0, ends[1], n_reads, out_taxon, out_span, stream);
+}
+
+int kid_pack_device(const kid_db *db, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                    uint64_t total_bases, size_t n_reads, uint32_t *words, size_t words_cap, uint32_t *meta,
+                    uint32_t *out_span, void *stream)
+{
+    if (!db || !meta) return fail(KID_EINVAL, "kid_pack_device: NULL argument");
+    if (n_reads && (!seq || !off || !words)) return fail(KID_EINVAL, "kid_pack_device: seq/off/words is NULL");
+    if ((reinterpret_cast<uintptr_t>(seq) & 15) || (reinterpret_cast<uintptr_t>(meta) & 7))
+        return fail(KID_EINVAL, "kid_pack_device: seq must be 16-byte aligned, meta 8-byte aligned");
+    const uint64_t bound = kid_pack_word_index(total_bases, n_reads) + 2;
+    if (bound >= 0x80000000ull || bound > words_cap)
+        return fail(KID_ERANGE, "kid_pack_device: %llu bases in %zu reads need %llu words (have %zu, limit 2^31)",
+                    (unsigned long long)total_bases, n_reads, (unsigned long long)bound, words_cap);
+    DeviceGuard guard(db->device);
+    KidPackParams pp;
+    pp.seq = seq;
+    pp.qual = qual;
+    pp.off = off;
+    pp.off_bias = 0;
+    pp.n_reads = n_reads;
+    pp.words = words;
+    pp.meta = reinterpret_cast<uint2 *>(meta);
+    pp.out_span = out_span;
+    pp.accept_u = (db->flags & KID_DB_ACCEPT_U) != 0;
+    KID_CUDA(kid_launch_pack(pp, db->sm_count, (cudaStream_t)stream));
+    return KID_OK;
+}
+
+int kid_classify_packed_device(kid_sample *s, const uint32_t *words, const uint32_t *meta, size_t n_reads,
+                               int32_t *out_taxon, void *stream)
+{
+    if (!s) return fail(KID_EINVAL, "kid_classify_packed_device: s is NULL");
+    if (n_reads == 0) return KID_OK;
+    if (!words || !meta) return fail(KID_EINVAL, "kid_classify_packed_device: words/meta is NULL");
+    if (reinterpret_cast<uintptr_t>(meta) & 7) return fail(KID_EINVAL, "kid_classify_packed_device: meta must be 8-byte aligned");
+    if (s->db->layout != KID_LAYOUT_MINIMIZER)
+        return fail(KID_EINVAL, "packed batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
+    DeviceGuard guard(s->db->device);
+    KidPackedParams p = make_packed_params(s, words, reinterpret_cast<const uint2 *>(meta), 0, n_reads, out_taxon);
+    KID_CUDA(kid_launch_classify3(p, s->db->sm_count, (cudaStream_t)stream));
     return KID_OK;
 }
 
@@ -527,31 +682,73 @@ int kid_sample_transfer_bytes(const kid_sample *s, uint64_t *h2d, uint64_t *d2h)
     return KID_OK;
 }
 
-static int slot_reserve(HostSlot &h, size_t bytes, size_t reads, bool want_qual)
+static int slot_open(kid_sample *s, HostSlot &h)
 {
     if (!h.stream) KID_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
-    if (bytes + 64 > h.cap_bytes || (want_qual && !h.qual)) {
-        KID_CUDA(cudaStreamSynchronize(h.stream));
-        cudaFree(h.seq); cudaFree(h.qual);
-        h.seq = h.qual = nullptr;
-        size_t cap = bytes + bytes / 4 + 64;
-        if (cap < h.cap_bytes) cap = h.cap_bytes;
-        h.cap_bytes = 0;
-        KID_CUDA(cudaMalloc(&h.seq, cap));
-        KID_CUDA(cudaMalloc(&h.qual, cap));
-        h.cap_bytes = cap;
+    // submissions must not overtake kid_sample_begin's memsets
+    KID_CUDA(cudaStreamWaitEvent(h.stream, s->begin_ev, 0));
+    return KID_OK;
+}
+
+// reads [r0, r0+n) of a host text batch: H2D, pack, scan, D2H on the slot's stream
+static int submit_text(kid_sample *s, HostSlot &h, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                       size_t r0, size_t n, int32_t *out_taxon, uint32_t *out_span)
+{
+    const uint64_t b0 = off[r0], bytes = off[r0 + n] - b0;
+    int rc = slot_open(s, h);
+    if (!rc) rc = reserve_text(h, (size_t)bytes, qual != nullptr);
+    if (!rc) rc = reserve_packed(h, 0, n);
+    if (rc) return rc;
+    KID_CUDA(cudaMemcpyAsync(h.seq, seq + b0, bytes, cudaMemcpyHostToDevice, h.stream));
+    if (qual) KID_CUDA(cudaMemcpyAsync(h.qual, qual + b0, bytes, cudaMemcpyHostToDevice, h.stream));
+    KID_CUDA(cudaMemcpyAsync(h.off, off + r0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h.stream));
+    s->h2d += bytes * (qual ? 2 : 1) + sizeof(uint64_t) * (n + 1);
+    if (use_fused_text_kernel(s->db)) {
+        KidClassifyParams p = make_params(s, h.seq, qual ? h.qual : nullptr, h.off, b0, n,
+                                          out_taxon ? h.out_taxon : nullptr, out_span ? h.out_span : nullptr);
+        KID_CUDA(launch_classify(s->db, p, h.stream));
+    } else {
+        rc = pack_and_scan(s, h, h.seq, qual ? h.qual : nullptr, h.off, b0, bytes, n, out_taxon ? h.out_taxon : nullptr,
+                           out_span ? h.out_span : nullptr, h.stream);
+        if (rc) return rc;
     }
-    if (reads > h.cap_reads) {
-        KID_CUDA(cudaStreamSynchronize(h.stream));
-        cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
-        h.off = nullptr; h.out_taxon = nullptr; h.out_span = nullptr;
-        h.cap_reads = 0;
-        const size_t cap = reads + reads / 4 + 16;
-        KID_CUDA(cudaMalloc(&h.off, sizeof(uint64_t) * (cap + 1)));
-        KID_CUDA(cudaMalloc(&h.out_taxon, sizeof(int32_t) * cap));
-        KID_CUDA(cudaMalloc(&h.out_span, sizeof(uint32_t) * 2 * cap));
-        h.cap_reads = cap;
+    if (out_taxon) {
+        KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
+        s->d2h += sizeof(int32_t) * n;
     }
+    if (out_span) {
+        KID_CUDA(cudaMemcpyAsync(out_span + 2 * r0, h.out_span, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, h.stream));
+        s->d2h += sizeof(uint32_t) * 2 * n;
+    }
+    return KID_OK;
+}
+
+// reads [r0, r0+n) of a host packed batch
+static int submit_packed(kid_sample *s, HostSlot &h, const uint32_t *words, uint32_t word0, const uint32_t *meta,
+                         size_t r0, size_t n, int32_t *out_taxon)
+{
+    const uint32_t wa = meta[2 * r0] & ~KID_PK_INVALID, wb = meta[2 * (r0 + n)] & ~KID_PK_INVALID;
+    if (wa < word0 || wb < wa) return fail(KID_EINVAL, "packed batch: word indices must be non-decreasing and >= word0");
+    const size_t nw = wb - wa;
+    int rc = slot_open(s, h);
+    if (!rc) rc = reserve_packed(h, nw, n);
+    if (rc) return rc;
+    if (nw) KID_CUDA(cudaMemcpyAsync(h.words, words + (wa - word0), sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, h.stream));
+    KID_CUDA(cudaMemcpyAsync(h.meta, meta + 2 * r0, sizeof(uint2) * (n + 1), cudaMemcpyHostToDevice, h.stream));
+    s->h2d += sizeof(uint32_t) * nw + sizeof(uint2) * (n + 1);
+    KidPackedParams p = make_packed_params(s, h.words, h.meta, wa, n, out_taxon ? h.out_taxon : nullptr);
+    KID_CUDA(kid_launch_classify3(p, s->db->sm_count, h.stream));
+    if (out_taxon) {
+        KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
+        s->d2h += sizeof(int32_t) * n;
+    }
+    return KID_OK;
+}
+
+static int sync_slots(kid_sample *s)
+{
+    for (HostSlot &h : s->slot)
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
     return KID_OK;
 }
 
@@ -565,32 +762,58 @@ int kid_classify_host(kid_sample *s, const uint8_t *seq, const uint8_t *qual, co
     int k = 0;
     for (size_t r0 = 0; r0 < n_reads; r0 += s->chunk_reads, k ^= 1) {
         const size_t n = (n_reads - r0 < s->chunk_reads) ? n_reads - r0 : s->chunk_reads;
-        const uint64_t b0 = off[r0], bytes = off[r0 + n] - b0;
-        HostSlot &h = s->slot[k];
-        int rc = slot_reserve(h, (size_t)bytes, n, qual != nullptr);
-        if (rc) return rc;
-        // the previous chunk on this slot must have drained before its buffers are overwritten
-        // (stream order guarantees it); the very first chunks wait for kid_sample_begin's memsets
-        KID_CUDA(cudaStreamWaitEvent(h.stream, s->begin_ev, 0));
-        KID_CUDA(cudaMemcpyAsync(h.seq, seq + b0, bytes, cudaMemcpyHostToDevice, h.stream));
-        if (qual) KID_CUDA(cudaMemcpyAsync(h.qual, qual + b0, bytes, cudaMemcpyHostToDevice, h.stream));
-        KID_CUDA(cudaMemcpyAsync(h.off, off + r0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h.stream));
-        s->h2d += bytes * (qual ? 2 : 1) + sizeof(uint64_t) * (n + 1);
-        KidClassifyParams p = make_params(s, h.seq, qual ? h.qual : nullptr, h.off, b0, n,
-                                          out_taxon ? h.out_taxon : nullptr,
-                                          out_span ? h.out_span : nullptr);
-        KID_CUDA(launch_classify(s->db, p, h.stream));
-        if (out_taxon) {
-            KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
-            s->d2h += sizeof(int32_t) * n;
-        }
-        if (out_span) {
-            KID_CUDA(cudaMemcpyAsync(out_span + 2 * r0, h.out_span, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, h.stream));
-            s->d2h += sizeof(uint32_t) * 2 * n;
-        }
+        // the previous chunk on this slot drains before its buffers are overwritten (stream order)
+        int rc = submit_text(s, s->slot[k], seq, qual, off, r0, n, out_taxon, out_span);
+        if (rc) { sync_slots(s); return rc; }
     }
-    for (HostSlot &h : s->slot)
-        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+    return sync_slots(s);
+}
+
+int kid_classify_packed_host(kid_sample *s, const uint32_t *words, uint32_t word0, const uint32_t *meta,
+                             size_t n_reads, int32_t *out_taxon)
+{
+    if (!s) return fail(KID_EINVAL, "kid_classify_packed_host: s is NULL");
+    if (n_reads == 0) return KID_OK;
+    if (!words || !meta) return fail(KID_EINVAL, "kid_classify_packed_host: words/meta is NULL");
+    if (s->db->layout != KID_LAYOUT_MINIMIZER)
+        return fail(KID_EINVAL, "packed batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
+    DeviceGuard guard(s->db->device);
+    int k = 0;
+    for (size_t r0 = 0; r0 < n_reads; r0 += s->chunk_reads, k ^= 1) {
+        const size_t n = (n_reads - r0 < s->chunk_reads) ? n_reads - r0 : s->chunk_reads;
+        int rc = submit_packed(s, s->slot[k], words, word0, meta, r0, n, out_taxon);
+        if (rc) { sync_slots(s); return rc; }
+    }
+    return sync_slots(s);
+}
+
+int kid_classify_async(kid_sample *s, int slot, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
+                       size_t n_reads, int32_t *out_taxon, uint32_t *out_span)
+{
+    if (!s || slot < 0 || slot >= KID_MAX_SLOTS) return fail(KID_EINVAL, "kid_classify_async: bad sample or slot");
+    if (n_reads == 0) return KID_OK;
+    if (!seq || !off) return fail(KID_EINVAL, "kid_classify_async: seq/off is NULL");
+    DeviceGuard guard(s->db->device);
+    return submit_text(s, s->slot[slot], seq, qual, off, 0, n_reads, out_taxon, out_span);
+}
+
+int kid_classify_packed_async(kid_sample *s, int slot, const uint32_t *words, uint32_t word0, const uint32_t *meta,
+                              size_t n_reads, int32_t *out_taxon)
+{
+    if (!s || slot < 0 || slot >= KID_MAX_SLOTS) return fail(KID_EINVAL, "kid_classify_packed_async: bad sample or slot");
+    if (n_reads == 0) return KID_OK;
+    if (!words || !meta) return fail(KID_EINVAL, "kid_classify_packed_async: words/meta is NULL");
+    if (s->db->layout != KID_LAYOUT_MINIMIZER)
+        return fail(KID_EINVAL, "packed batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
+    DeviceGuard guard(s->db->device);
+    return submit_packed(s, s->slot[slot], words, word0, meta, 0, n_reads, out_taxon);
+}
+
+int kid_wait(kid_sample *s, int slot)
+{
+    if (!s || slot < 0 || slot >= KID_MAX_SLOTS) return fail(KID_EINVAL, "kid_wait: bad sample or slot");
+    DeviceGuard guard(s->db->device);
+    if (s->slot[slot].stream) KID_CUDA(cudaStreamSynchronize(s->slot[slot].stream));
     return KID_OK;
 }
 

@@ -1,0 +1,372 @@
+// kid_classify3.cu - the per-read hot path over PACKED read batches (kid_kernels.cuh) and the
+// minimizer-addressed table (kid_table2.cuh).
+//
+// Replaces, for a whole batch of reads, process_read (newkmer_10nx.cpp:452-617), Hashtable::getHash
+// (:204-233) and Tree1::msca (:118-144).  process_qual's trim (:714-760) and the ACGT test (:480-524)
+// happened when the batch was packed (kid_pack.cu on the device, kid_pack_reads on a host parser), so a
+// read arrives as `tlen` 2-bit codes that start on a word boundary, plus validity words only if it
+// contains a base outside ACGTacgt.
+//
+// Persistent grid, one 1024-thread block per SM; a warp takes kGroup consecutive reads at a time and
+// lane j of chunk c owns the k-mer that starts at base 32c+j of the current read.
+//   STAGE   the group's words go from global to a per-warp shared-memory strip with coalesced 4-byte
+//           loads (as many reads of the group as fit the strip at once; a read that is longer than
+//           the strip is walked in windows).
+//   KEYS    two LDS + funnel shifts give the 64 bits that start at the lane's base: the top 32 are
+//           its 16-mer (minimizer candidate), the top 60 its forward k-mer (:481-517); __brev gives
+//           the reverse complement, min() the canonical key (:528).  A block covers 4 chunks
+//           (128 k-mers, a whole 150-base read): the 16-mer hashes of 5 chunk positions are computed
+//           once (the fifth is the 14-lane halo of the fourth).
+//   MINIM   sliding minimum of the 16-mer hashes over 15 positions: 4 shuffle rounds (1,2,4,7).
+//   LOOKUP  sector = group(M) | sector(key); two chunks (64 k-mers) request their 32-byte sectors
+//           before the first is consumed, then the other two.  Lanes that share a minimizer share a
+//           128-byte line, so a warp-wide load touches ~5 lines instead of 32.
+//   FOLD    hits are rare; a ballot finds them and the warp folds them strictly in position order
+//           with kid_msca (the fold is order dependent).
+//   COUNT   seen bit (atomicOr on the per-sample bitmap) for hits with taxon > 1 (:596-603),
+//           gcount[final]++ (:613) in a shared-memory histogram flushed once per block.
+#include "kid_kernels.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
+constexpr int kStripWords = 128;  // code words a staged run of reads may span (2048 bases)
+constexpr int kStripPad = 12;     // zero words behind them: halo lanes never need a bounds check
+constexpr int kMaskWords = 72;    // "a run of 30 valid bases starts here" bits of ONE read / window
+constexpr int kGroup = 6;         // consecutive reads a warp fetches the metadata of together
+constexpr int kLongStarts = 1920; // k-mer starts per window of a read longer than the strip (120 words)
+
+struct WarpStrip {
+    uint32_t codes[kStripWords + kStripPad];
+    uint32_t kmask[kMaskWords];
+};
+
+__device__ __forceinline__ uint32_t ld_words(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// kmask of one read (or one window of a long read) from its validity words v[0..nv): bit 31-(j&31) of
+// word j>>5 says that bases j..j+29 are all ACGT (cpos == KSIZE at base j+29, :526)
+__device__ __forceinline__ void build_kmask(WarpStrip &strip, const uint32_t *v, int nv, int n_out, int lane)
+{
+    __syncwarp();
+    for (int i = lane; i < n_out; i += 32) {
+        const uint32_t a = i < nv ? __ldg(v + i) : 0u, b = i + 1 < nv ? __ldg(v + i + 1) : 0u;
+        uint64_t x = ((uint64_t)a << 32) | b;
+        x &= x << 1; x &= x << 2; x &= x << 4; x &= x << 8; // runs of 16
+        x &= x << 14;                                       // runs of 30
+        strip.kmask[i] = (uint32_t)(x >> 32);
+    }
+    __syncwarp();
+}
+
+struct ScanState {
+    uint32_t fin;               // running final taxon of the read (:588-595)
+    unsigned lane_lookups;      // per lane, reduced once at the end of the kernel
+    unsigned long long n_hits;  // warp-uniform
+};
+
+// LOOKUP .. FOLD for two chunks of 32 k-mers
+__device__ __forceinline__ void lookup_pair(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t (&key)[2],
+                                            const uint32_t (&mn)[2], const bool (&act)[2], ScanState &st)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    uint4 ea[2], eb[2];
+    uint32_t sec[2];
+    // every sector load is issued before any is consumed.  Inactive lanes (k-mer with an N, or outside
+    // the read) read sector 0 instead of branching; their result is ignored.
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const uint32_t grp = (mn[u] * 0x9E3779B1u) >> tab.line_shift;
+        sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
+        kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
+    }
+    bool hit[2];
+    uint32_t again = 0;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+        const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
+                       (eb[u].x == klo && eb[u].y == khi);
+        hit[u] = act[u] && h;
+        // all three entries carry bit 63 and none matched: the key may live further on
+        const bool more = act[u] && !h && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
+        again |= more ? (1u << u) : 0u;
+    }
+    if (__any_sync(full, again != 0)) { // the few lanes that met a full sector: all loads first
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+            kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if ((again >> u) & 1u) {
+                const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                uint32_t tx = 0;
+                int j = 0;
+                const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
+                if (res > 0) {
+                    hit[u] = true;
+                    sec[u] = sec[u] + 1; // slack sectors follow the last home sector
+                } else if (res < 0) { // rare: third sector and on
+                    uint64_t slot = 0;
+                    if (kid2_lookup_from(tab, sec[u], key[u], 2, slot)) {
+                        hit[u] = true;
+                        sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
+                        kid2_load_sector(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u]);
+                    }
+                }
+            }
+        }
+    }
+    // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        unsigned m = __ballot_sync(full, hit[u]);
+        if (m) {
+            uint32_t taxon = 0;
+            if (hit[u]) {
+                const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                int j = 0;
+                kid2_match(ea[u], eb[u], klo, khi, taxon, j);
+                if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
+                    const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
+                    atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                }
+            }
+            st.n_hits += __popc(m);
+            do { // ordered left fold over the hits of this chunk (:588-595)
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t tj = __shfl_sync(full, taxon, src);
+                if (st.fin > 0) { if (tj != st.fin) st.fin = kid_msca(p.tree, tj, st.fin); }
+                else st.fin = tj;
+            } while (m);
+        }
+    }
+}
+
+// KEYS .. FOLD over the k-mers that start at positions [c, c+128) of a read whose first base sits at
+// staged index tbase; `last` = its last k-mer start; kmask bits apply only when `flagged`
+__device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2TableView &tab, const WarpStrip &strip,
+                                           int tbase, int c, int last, bool flagged, int lane, ScanState &st)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const int t0 = tbase + c + lane; // staged index of this lane's base in chunk 0; chunk u: + 32u
+    const uint32_t *cw = strip.codes + (t0 >> 4);
+    const int sh = (t0 & 15) * 2;
+    uint32_t W[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) W[i] = cw[i];
+    uint32_t cm[5]; // 16-mer hashes -> sliding minima
+    uint64_t key[4];
+#pragma unroll
+    for (int u = 0; u < 5; u++) {
+        const uint32_t hi = __funnelshift_l(W[2 * u + 1], W[2 * u], sh);
+        const uint32_t rc = kid_rc16(hi);
+        cm[u] = kid_mm_hash_canon(min(hi, rc));
+        if (u < 4) {
+            // forward key = first 30 of the 32 bases at this position; the reverse complement of 32
+            // bases is rc16(low half) : rc16(high half), its low 60 bits that of the first 30 bases
+            const uint32_t lo = __funnelshift_l(W[2 * u + 2], W[2 * u + 1], sh);
+            const uint64_t kf = (((uint64_t)hi << 32) | lo) >> 4;
+            const uint64_t kr = (((uint64_t)kid_rc16(lo) << 32) | rc) & KID_MASK60;
+            key[u] = kf < kr ? kf : kr; // :528
+        }
+    }
+    // MINIM: window minimum over 15 consecutive positions (1 + 2 + 4 + 7 doubling)
+#pragma unroll
+    for (int step = 0; step < 4; step++) {
+        const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
+        const int src = lane + d; // shfl takes the source lane modulo 32
+        const bool wrap = lane + d >= 32;
+        uint32_t s[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) s[u] = __shfl_sync(full, cm[u], src);
+#pragma unroll
+        for (int u = 0; u < 4; u++) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
+        if (step < 3) cm[4] = min(cm[4], wrap ? 0xFFFFFFFFu : s[4]);
+    }
+    bool act[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = c + 32 * u + lane;
+        bool a = j <= last;
+        if (flagged) a = a && (int32_t)(strip.kmask[(c >> 5) + u] << lane) < 0;
+        act[u] = a;
+        st.lane_lookups += a; // each is one getHash call (:529)
+    }
+    {
+        const uint64_t k2[2] = { key[0], key[1] };
+        const uint32_t m2[2] = { cm[0], cm[1] };
+        const bool a2[2] = { act[0], act[1] };
+        lookup_pair(p, tab, k2, m2, a2, st);
+    }
+    if (c + 64 <= last) { // warp-uniform
+        const uint64_t k2[2] = { key[2], key[3] };
+        const uint32_t m2[2] = { cm[2], cm[3] };
+        const bool a2[2] = { act[2], act[3] };
+        lookup_pair(p, tab, k2, m2, a2, st);
+    }
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 1)
+kid_classify3_kernel(const KidPackedParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpStrip *strips = reinterpret_cast<WarpStrip *>(smem_raw);
+    int *hist = reinterpret_cast<int *>(smem_raw + sizeof(WarpStrip) * kWarpsPerBlock);
+
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    WarpStrip &strip = strips[warp_in_block];
+    const Kid2TableView tab = p.table2;
+
+    if (SMEM_HIST) {
+        for (int i = threadIdx.x; i < p.tree.n_taxa; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    if (lane < kStripPad) strip.codes[kStripWords + lane] = 0;
+
+    ScanState st;
+    st.fin = 0;
+    st.lane_lookups = 0;
+    st.n_hits = 0;
+
+    auto finish_read = [&](size_t r, bool kept) { // per-read output and gcount[final]++ (:613)
+        if (lane == 0) {
+            if (p.out_taxon) p.out_taxon[r] = kept ? (int32_t)st.fin : -1;
+            if (kept) {
+                if (SMEM_HIST) atomicAdd(&hist[st.fin], 1);
+                else atomicAdd(&p.gcount[st.fin], 1);
+            }
+        }
+    };
+
+    const size_t n_groups = (p.n_reads + kGroup - 1) / kGroup;
+    const size_t warps_total = (size_t)gridDim.x * kWarpsPerBlock;
+    for (size_t grp = (size_t)blockIdx.x * kWarpsPerBlock + warp_in_block; grp < n_groups; grp += warps_total) {
+        const size_t r0 = grp * kGroup;
+        const int nr = (int)min((size_t)kGroup, p.n_reads - r0);
+        // lane i holds read r0+i: first word (relative to the batch), length, flag; lane nr the end
+        uint32_t w_first = 0, tlen = 0;
+        if (lane <= nr) {
+            const uint2 m = __ldg(p.meta + r0 + lane);
+            w_first = m.x;
+            tlen = m.y;
+        }
+        const bool my_flag = (w_first & KID_PK_FLAG) != 0;
+        w_first = (w_first & ~KID_PK_FLAG) - p.word_bias;
+        // words this read occupies: codes + validity words if flagged
+        const uint32_t my_words = lane < nr ? ((tlen + 15) >> 4) + (my_flag ? (tlen + 31) >> 5 : 0u) : 0u;
+        const uint32_t w_end = w_first + my_words;
+
+        int s = 0;
+        while (s < nr) {
+            const uint32_t base = __shfl_sync(full, w_first, s);
+            // reads s..e-1 are staged together: the largest run whose words end inside the strip
+            const unsigned fits = __ballot_sync(full, lane >= s && lane < nr && w_end - base <= (uint32_t)kStripWords);
+            const int e = s + __popc(fits & ~((1u << s) - 1u) & (~fits + (1u << s))); // leading run of ones from bit s
+            if (e > s) {
+                const uint32_t span = __shfl_sync(full, w_end, e - 1) - base;
+                __syncwarp();
+                for (uint32_t i = lane; i < span; i += 32) strip.codes[i] = ld_words(p.words + base + i);
+                __syncwarp();
+                for (int i = s; i < e; i++) {
+                    const int tl = (int)__shfl_sync(full, tlen, i);
+                    const uint32_t wf = __shfl_sync(full, w_first, i);
+                    const bool flagged = __shfl_sync(full, (int)my_flag, i) != 0;
+                    const bool kept = tl > KID_KSIZE; // stop - start >= KSIZE (:755)
+                    st.fin = 0;
+                    if (kept) {
+                        const int last = tl - KID_KSIZE;
+                        if (flagged) build_kmask(strip, p.words + wf + ((tl + 15) >> 4), (tl + 31) >> 5, (last >> 5) + 1, lane);
+                        const int tbase = (int)(wf - base) * 16;
+                        for (int c = 0; c <= last; c += 128) scan_block(p, tab, strip, tbase, c, last, flagged, lane, st);
+                    }
+                    finish_read(r0 + i, kept);
+                }
+                s = e;
+                continue;
+            }
+            // ---- read s alone does not fit the strip: windows of kLongStarts k-mer starts
+            {
+                const int tl = (int)__shfl_sync(full, tlen, s);
+                const uint32_t wf = __shfl_sync(full, w_first, s);
+                const bool flagged = __shfl_sync(full, (int)my_flag, s) != 0;
+                const bool kept = tl > KID_KSIZE;
+                st.fin = 0;
+                if (kept) {
+                    const int last = tl - KID_KSIZE;
+                    const int cwords = (tl + 15) >> 4, vwords = (tl + 31) >> 5;
+                    for (int wb = 0; wb <= last; wb += kLongStarts) {
+                        const int wlast = min(kLongStarts - 1, last - wb);
+                        const int w0 = wb >> 4, nw = min(kStripWords, cwords - w0);
+                        __syncwarp();
+                        for (int i = lane; i < kStripWords; i += 32) strip.codes[i] = i < nw ? ld_words(p.words + wf + w0 + i) : 0u;
+                        __syncwarp();
+                        if (flagged)
+                            build_kmask(strip, p.words + wf + cwords + (wb >> 5), vwords - (wb >> 5), (wlast >> 5) + 1, lane);
+                        for (int c = 0; c <= wlast; c += 128) scan_block(p, tab, strip, 0, c, wlast, flagged, lane, st);
+                    }
+                }
+                finish_read(r0 + s, kept);
+                s++;
+            }
+        }
+    }
+
+    unsigned long long n_lookups = st.lane_lookups;
+    for (int o = 16; o; o >>= 1) n_lookups += __shfl_xor_sync(full, n_lookups, o);
+    if (lane == 0) {
+        if (n_lookups) atomicAdd(p.counters + 0, n_lookups);
+        if (st.n_hits) atomicAdd(p.counters + 1, st.n_hits);
+    }
+    if (SMEM_HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.tree.n_taxa; i += blockDim.x) {
+            const int cnt = hist[i];
+            if (cnt) atomicAdd(&p.gcount[i], cnt);
+        }
+    }
+}
+
+template <bool H>
+cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stream)
+{
+    const size_t smem = sizeof(WarpStrip) * kWarpsPerBlock + (H ? (size_t)p.tree.n_taxa * 4 : 0);
+    auto kern = kid_classify3_kernel<H>;
+    cudaError_t err = cudaSuccess;
+    if (smem > 48 * 1024) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
+    // shared memory and L1 are one 256 KB array: reserve only what the block uses, the rest caches
+    // the taxonomy rows
+    if (getenv("KID_NO_CARVEOUT") == nullptr) {
+        int pct = (int)(((smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct); // a hint: failure is harmless
+    }
+    size_t blocks = (size_t)sm_count; // persistent: one block per SM
+    const size_t need = ((p.n_reads + kGroup - 1) / kGroup + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > need) blocks = need;
+    if (blocks == 0) return cudaSuccess;
+    kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStream_t stream)
+{
+    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
+    return hist ? launch_one<true>(p, sm_count, stream) : launch_one<false>(p, sm_count, stream);
+}

@@ -33,6 +33,49 @@ struct KidClassifyParams {
     bool accept_u;
 };
 
+// ---- packed read batches --------------------------------------------------------------------------
+// What the k-mer scan consumes (include/kmer_id.h, "packed read batches"): per read the TRIMMED bases
+// as 2-bit codes, 16 per 32-bit word with the first base in the top pair (A 0, C 1, G 2, T 3, anything
+// else 0), zero padded to a whole word; reads that contain a non-ACGT base carry KID_PK_FLAG and are
+// followed by ceil(tlen/32) validity words (first base in the top bit, 1 = ACGT).
+//   meta[r] = { first word of read r | KID_PK_FLAG, tlen }     r = 0..n_reads (entry n_reads = end)
+// tlen = stop - start + 1 of process_qual (newkmer_10nx.cpp:714-760); a read is classified iff
+// tlen >= 31 (:755).  Words need not be dense: kid_pack.cu leaves gaps, a host packer does not.
+#define KID_PK_FLAG 0x80000000u
+struct KidPackedParams {
+    Kid2TableView table2;
+    KidTreeView tree;
+    const uint32_t *words;
+    const uint2 *meta;  // n_reads + 1
+    uint32_t word_bias; // subtracted from every meta[].x word index (chunked host batches)
+    size_t n_reads;
+    int32_t *out_taxon; // may be NULL
+    int *gcount;
+    uint32_t *seen;
+    unsigned long long *counters; // [0] lookups, [1] hits
+};
+cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStream_t stream);
+
+// raw bytes -> packed batch on the device (kid_pack.cu): process_qual's trim + ACGT test + 2-bit pack.
+// Read r gets the words starting at (off[r]-bias)/16 + (off[r]-bias)/32 + 2r (room for its validity
+// words whether it needs them or not), so no prefix sum is needed.
+struct KidPackParams {
+    const uint8_t *seq;
+    const uint8_t *qual; // NULL: no trimming (FASTA)
+    const uint64_t *off; // n_reads + 1
+    uint64_t off_bias;
+    size_t n_reads;
+    uint32_t *words;     // kid_pack_words_bound(bytes, n_reads) entries
+    uint2 *meta;         // n_reads + 1
+    uint32_t *out_span;  // may be NULL: {start, stop} per read as process_qual leaves them
+    bool accept_u;
+};
+__host__ __device__ __forceinline__ uint64_t kid_pack_word_index(uint64_t rel_off, uint64_t r)
+{
+    return (rel_off >> 4) + (rel_off >> 5) + 2 * r;
+}
+cudaError_t kid_launch_pack(const KidPackParams &p, int sm_count, cudaStream_t stream);
+
 // every kernel launch of this library bumps this (bench.py reports it as gpu_launches)
 extern unsigned long long g_kid_kernel_launches;
 #define KID_COUNT_LAUNCH() (__atomic_add_fetch(&g_kid_kernel_launches, 1ULL, __ATOMIC_RELAXED))
