@@ -73,6 +73,7 @@ def parse_args():
                     help="skip the gz-files-on-disk -> _result.txt run of the nk10 drop-in")
     ap.add_argument("--layout", default="M", choices=["M", "K"], help="table layout (M = minimizer, default)")
     ap.add_argument("--log2-sectors", type=int, default=0, help="table size override (0 = library default)")
+    ap.add_argument("--chunk-reads", type=int, default=0, help="reads per H2D chunk of the host entry points (0 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=80.0,
                     help="CPU seconds the reference arm may spend classifying (all steps together)")
     ap.add_argument("--ref-den", type=int, default=1,
@@ -293,6 +294,8 @@ def run_ours(args):
     doff = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * READ_LEN
     dout = torch.empty(n_reads, dtype=torch.int32, device=dev)
     sample = kid.Sample(db)
+    if args.chunk_reads:
+        sample.set_chunk_reads(args.chunk_reads)
     engine, transport = multi_gpu.make_engine(sample, stream, prefer_peer=os.environ.get("KID_PEER", "1") != "0")
     torch.cuda.synchronize()
 

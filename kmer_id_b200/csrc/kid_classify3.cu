@@ -35,7 +35,7 @@ constexpr int kWarpsPerBlock = KID_CLASSIFY_THREADS / 32;
 constexpr int kStripWords = 128;  // code words a staged run of reads may span (2048 bases)
 constexpr int kStripPad = 12;     // zero words behind them: halo lanes never need a bounds check
 constexpr int kMaskWords = 72;    // "a run of 30 valid bases starts here" bits of ONE read / window
-constexpr int kGroup = 6;         // consecutive reads a warp fetches the metadata of together
+constexpr int kGroupDefault = 8;  // consecutive reads a warp fetches the metadata of together (6: 16.90 ms, 8: 16.78, 12: 16.76)
 constexpr int kLongStarts = 1920; // k-mer starts per window of a read longer than the strip (120 words)
 
 struct WarpStrip {
@@ -65,31 +65,44 @@ __device__ __forceinline__ void build_kmask(WarpStrip &strip, const uint32_t *v,
     __syncwarp();
 }
 
-struct ScanState {
-    uint32_t fin;               // running final taxon of the read (:588-595)
-    unsigned lane_lookups;      // per lane, reduced once at the end of the kernel
-    unsigned long long n_hits;  // warp-uniform
+// the three keys of a sector without its taxa words: 6 registers instead of 8 (the taxa are fetched
+// again for the rare hit), which is what lets four chunks be in flight at 64 registers
+__device__ __forceinline__ void load_sector_keys(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(p + 1));
+}
+
+struct ScanState { // all warp-uniform
+    uint32_t fin;                 // running final taxon of the read (:588-595)
+    unsigned long long n_lookups; // getHash calls (:529)
+    unsigned long long n_hits;
 };
 
-// LOOKUP .. FOLD for two chunks of 32 k-mers
-__device__ __forceinline__ void lookup_pair(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t (&key)[2],
-                                            const uint32_t (&mn)[2], const bool (&act)[2], ScanState &st)
+// LOOKUP .. FOLD for N chunks of 32 k-mers whose sector indices are known: all N sector loads are in
+// flight before the first is consumed
+template <int N, bool kKeysOnly, bool kL1>
+__device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t *key,
+                                              uint32_t *sec, const bool *act, ScanState &st)
 {
     const unsigned full = 0xFFFFFFFFu;
-    uint4 ea[2], eb[2];
-    uint32_t sec[2];
-    // every sector load is issued before any is consumed.  Inactive lanes (k-mer with an N, or outside
-    // the read) read sector 0 instead of branching; their result is ignored.
+    uint4 ea[N], eb[N];
+    // Inactive lanes (k-mer with an N, or outside the read) read sector 0 instead of branching; their
+    // result is ignored.
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const uint32_t grp = (mn[u] * 0x9E3779B1u) >> tab.line_shift;
-        sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
-        kid2_load_sector(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u), ea[u], eb[u]);
+    for (int u = 0; u < N; u++) {
+        const uint4 *sp = tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u);
+        if (kKeysOnly) load_sector_keys(sp, ea[u], eb[u]);
+        else if (kL1) // the sector was prefetched into L1
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(ea[u].x), "=r"(ea[u].y), "=r"(ea[u].z), "=r"(ea[u].w), "=r"(eb[u].x), "=r"(eb[u].y), "=r"(eb[u].z), "=r"(eb[u].w)
+                         : "l"(sp));
+        else kid2_load_sector(sp, ea[u], eb[u]);
     }
-    bool hit[2];
+    bool hit[N];
     uint32_t again = 0;
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < N; u++) {
         const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
         const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
                        (eb[u].x == klo && eb[u].y == khi);
@@ -100,10 +113,10 @@ __device__ __forceinline__ void lookup_pair(const KidPackedParams &p, const Kid2
     }
     if (__any_sync(full, again != 0)) { // the few lanes that met a full sector: all loads first
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+        for (int u = 0; u < N; u++)
             kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < N; u++) {
             if ((again >> u) & 1u) {
                 const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
                 uint32_t tx = 0;
@@ -125,13 +138,18 @@ __device__ __forceinline__ void lookup_pair(const KidPackedParams &p, const Kid2
     }
     // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < N; u++) {
         unsigned m = __ballot_sync(full, hit[u]);
         if (m) {
             uint32_t taxon = 0;
             if (hit[u]) {
                 const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
                 int j = 0;
+                if (kKeysOnly) { // whichever sector the key was found in: fetch its taxa words now
+                    const uint2 tw = __ldg(reinterpret_cast<const uint2 *>(tab.sectors + 2 * (uint64_t)sec[u]) + 3);
+                    eb[u].z = tw.x;
+                    eb[u].w = tw.y;
+                }
                 kid2_match(ea[u], eb[u], klo, khi, taxon, j);
                 if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
                     const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
@@ -152,6 +170,7 @@ __device__ __forceinline__ void lookup_pair(const KidPackedParams &p, const Kid2
 
 // KEYS .. FOLD over the k-mers that start at positions [c, c+128) of a read whose first base sits at
 // staged index tbase; `last` = its last k-mer start; kmask bits apply only when `flagged`
+template <int kInFlight, int kPrefetch>
 __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2TableView &tab, const WarpStrip &strip,
                                            int tbase, int c, int last, bool flagged, int lane, ScanState &st)
 {
@@ -191,30 +210,42 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
         for (int u = 0; u < 4; u++) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
         if (step < 3) cm[4] = min(cm[4], wrap ? 0xFFFFFFFFu : s[4]);
     }
+    // which of the 128 positions are k-mer starts: inside the read (first nv positions of the block)
+    // and, for a read with non-ACGT bases, the start of a run of 30 valid bases.  Warp-uniform masks,
+    // position 32u+j in bit 31-j of word u.
     bool act[4];
+    uint32_t sec[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-        const int j = c + 32 * u + lane;
-        bool a = j <= last;
-        if (flagged) a = a && (int32_t)(strip.kmask[(c >> 5) + u] << lane) < 0;
-        act[u] = a;
-        st.lane_lookups += a; // each is one getHash call (:529)
+        const int nv = last - c - 32 * u + 1;
+        uint32_t m = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : 0xFFFFFFFFu << (32 - nv));
+        if (flagged) m &= strip.kmask[(c >> 5) + u];
+        st.n_lookups += __popc(m); // each is one getHash call (:529)
+        act[u] = (int32_t)(m << lane) < 0;
+        const uint32_t grp = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
+        sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
     }
-    {
-        const uint64_t k2[2] = { key[0], key[1] };
-        const uint32_t m2[2] = { cm[0], cm[1] };
-        const bool a2[2] = { act[0], act[1] };
-        lookup_pair(p, tab, k2, m2, a2, st);
-    }
-    if (c + 64 <= last) { // warp-uniform
-        const uint64_t k2[2] = { key[2], key[3] };
-        const uint32_t m2[2] = { cm[2], cm[3] };
-        const bool a2[2] = { act[2], act[3] };
-        lookup_pair(p, tab, k2, m2, a2, st);
+    if (kInFlight == 4) {
+        lookup_chunks<4, true, false>(p, tab, key, sec, act, st);
+    } else {
+        // every sector index is known before the first load goes out, so that the compiler cannot
+        // slide the tail of MINIM between the two loads of the first pair
+        asm volatile("" ::"r"(sec[0]), "r"(sec[1]), "r"(sec[2]), "r"(sec[3]));
+        const bool second = c + 64 <= last; // warp-uniform
+        if (kPrefetch && second) {
+#pragma unroll
+            for (int u = 2; u < 4; u++) {
+                const uint4 *sp = tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u);
+                if (kPrefetch == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+                else asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+            }
+        }
+        lookup_chunks<2, false, false>(p, tab, key, sec, act, st);
+        if (second) lookup_chunks<2, false, kPrefetch == 2>(p, tab, key + 2, sec + 2, act + 2, st);
     }
 }
 
-template <bool SMEM_HIST>
+template <bool SMEM_HIST, int kInFlight, int kPrefetch, int kGroup>
 __global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 1)
 kid_classify3_kernel(const KidPackedParams p)
 {
@@ -236,7 +267,7 @@ kid_classify3_kernel(const KidPackedParams p)
 
     ScanState st;
     st.fin = 0;
-    st.lane_lookups = 0;
+    st.n_lookups = 0;
     st.n_hits = 0;
 
     auto finish_read = [&](size_t r, bool kept) { // per-read output and gcount[final]++ (:613)
@@ -272,7 +303,7 @@ kid_classify3_kernel(const KidPackedParams p)
             const uint32_t base = __shfl_sync(full, w_first, s);
             // reads s..e-1 are staged together: the largest run whose words end inside the strip
             const unsigned fits = __ballot_sync(full, lane >= s && lane < nr && w_end - base <= (uint32_t)kStripWords);
-            const int e = s + __popc(fits & ~((1u << s) - 1u) & (~fits + (1u << s))); // leading run of ones from bit s
+            const int e = s + __popc(fits); // word indices do not decrease, so the lanes that fit are s..e-1
             if (e > s) {
                 const uint32_t span = __shfl_sync(full, w_end, e - 1) - base;
                 __syncwarp();
@@ -288,7 +319,7 @@ kid_classify3_kernel(const KidPackedParams p)
                         const int last = tl - KID_KSIZE;
                         if (flagged) build_kmask(strip, p.words + wf + ((tl + 15) >> 4), (tl + 31) >> 5, (last >> 5) + 1, lane);
                         const int tbase = (int)(wf - base) * 16;
-                        for (int c = 0; c <= last; c += 128) scan_block(p, tab, strip, tbase, c, last, flagged, lane, st);
+                        for (int c = 0; c <= last; c += 128) scan_block<kInFlight, kPrefetch>(p, tab, strip, tbase, c, last, flagged, lane, st);
                     }
                     finish_read(r0 + i, kept);
                 }
@@ -313,7 +344,7 @@ kid_classify3_kernel(const KidPackedParams p)
                         __syncwarp();
                         if (flagged)
                             build_kmask(strip, p.words + wf + cwords + (wb >> 5), vwords - (wb >> 5), (wlast >> 5) + 1, lane);
-                        for (int c = 0; c <= wlast; c += 128) scan_block(p, tab, strip, 0, c, wlast, flagged, lane, st);
+                        for (int c = 0; c <= wlast; c += 128) scan_block<kInFlight, kPrefetch>(p, tab, strip, 0, c, wlast, flagged, lane, st);
                     }
                 }
                 finish_read(r0 + s, kept);
@@ -322,10 +353,8 @@ kid_classify3_kernel(const KidPackedParams p)
         }
     }
 
-    unsigned long long n_lookups = st.lane_lookups;
-    for (int o = 16; o; o >>= 1) n_lookups += __shfl_xor_sync(full, n_lookups, o);
     if (lane == 0) {
-        if (n_lookups) atomicAdd(p.counters + 0, n_lookups);
+        if (st.n_lookups) atomicAdd(p.counters + 0, st.n_lookups);
         if (st.n_hits) atomicAdd(p.counters + 1, st.n_hits);
     }
     if (SMEM_HIST) {
@@ -337,11 +366,11 @@ kid_classify3_kernel(const KidPackedParams p)
     }
 }
 
-template <bool H>
+template <bool H, int F, int PF, int G>
 cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WarpStrip) * kWarpsPerBlock + (H ? (size_t)p.tree.n_taxa * 4 : 0);
-    auto kern = kid_classify3_kernel<H>;
+    auto kern = kid_classify3_kernel<H, F, PF, G>;
     cudaError_t err = cudaSuccess;
     if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -355,7 +384,7 @@ cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stre
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct); // a hint: failure is harmless
     }
     size_t blocks = (size_t)sm_count; // persistent: one block per SM
-    const size_t need = ((p.n_reads + kGroup - 1) / kGroup + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t need = ((p.n_reads + G - 1) / G + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > need) blocks = need;
     if (blocks == 0) return cudaSuccess;
     kern<<<(unsigned)blocks, KID_CLASSIFY_THREADS, smem, stream>>>(p);
@@ -363,10 +392,31 @@ cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stre
     return cudaGetLastError();
 }
 
+template <int F, int PF, int G = kGroupDefault>
+cudaError_t launch_variant(const KidPackedParams &p, int sm_count, cudaStream_t stream)
+{
+    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
+    return hist ? launch_one<true, F, PF, G>(p, sm_count, stream) : launch_one<false, F, PF, G>(p, sm_count, stream);
+}
+
 } // namespace
 
 cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStream_t stream)
 {
-    const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
-    return hist ? launch_one<true>(p, sm_count, stream) : launch_one<false>(p, sm_count, stream);
+    // Measured on B200 (bact10-scale table, 20 M 150-base reads, tools/gpu_b.sh): two chunks in flight,
+    // then the other two: 16.9 ms; the same with the second pair prefetched into L1: 16.9 ms, into L2:
+    // 22.9 ms; all four in flight with key-only loads (6 registers per sector): 25.7 ms.
+#ifdef KID_TUNE_VARIANTS // experiment builds only: KID_TUNE=<n> picks how the 4 chunks of a block are looked up
+    static const int tune = getenv("KID_TUNE") ? atoi(getenv("KID_TUNE")) : 0;
+    switch (tune) {
+    case 1: return launch_variant<2, 1>(p, sm_count, stream); // the other 2 prefetched into L2
+    case 2: return launch_variant<4, 0>(p, sm_count, stream); // all 4 in flight (keys only)
+    case 3: return launch_variant<2, 2>(p, sm_count, stream); // the other 2 prefetched into L1
+    case 4: return launch_variant<2, 0, 8>(p, sm_count, stream);  // 8 reads per group
+    case 5: return launch_variant<2, 0, 12>(p, sm_count, stream); // 12 reads per group
+    case 6: return launch_variant<2, 0, 3>(p, sm_count, stream);  // 3 reads per group
+    default: break;
+    }
+#endif
+    return launch_variant<2, 0>(p, sm_count, stream);
 }

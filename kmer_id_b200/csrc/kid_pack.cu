@@ -3,28 +3,30 @@
 // Replaces process_qual (newkmer_10nx.cpp:714-760) and the per-base switch of process_read
 // (:477-525) for a whole batch: trim each read by its qualities, test every base of the trimmed
 // span for ACGTacgt (+Uu), and write the span as 2-bit codes that start on a word boundary, plus
-// validity words when a base fails the test.  A streaming kernel: 2 x L bytes in, ~L/4 bytes out per
-// read; the k-mer scan (kid_classify3.cu) then never touches text or qualities.
+// validity words.  A streaming kernel; the k-mer scan (kid_classify3.cu) then never touches text or
+// qualities.
 //
-// A warp takes 3 consecutive reads at a time; when they fit one 512-base window (always for 150-bp
-// reads) they are loaded with one coalesced 128-bit load per lane, and every read's first / last 32
-// quality bytes are requested before any is used.  Longer reads are walked in windows of 480 bases
-// and always carry validity words.
+// A warp takes 32 consecutive reads at a time.
+//   TRIM  one lane per read: a read whose first and last quality byte and 4-base window pass (nearly
+//         all good reads) is decided from 8 bytes; the others go through the warp-cooperative search
+//         of kid_readprep.cuh one after the other.
+//   PACK  one lane per 32 bases of trimmed sequence, over all 32 reads (a prefix sum of the reads'
+//         unit counts in shared memory, a 5-step binary search per unit): nine aligned 32-bit loads,
+//         byte realignment with funnel shifts, SIMD-in-word packing (kid_readprep.cuh) -> two code
+//         words and one validity word.  Reads of any length take the same path.
 #include "kid_kernels.cuh"
 #include "kid_readprep.cuh"
 
 namespace {
 
 constexpr int kPackThreads = 256;
-constexpr int kCodeWords = 36;  // 32 + zero padding
-constexpr int kValidWords = 20; // 16 + zero padding
-constexpr int kGroup = 3;
-constexpr int kGroupMaxSpan = 496;
-constexpr int kLongStep = 480; // bases per window of the long path: 30 code words, 15 validity words
 
-struct PackStrip {
-    uint32_t codes[kCodeWords];
-    uint32_t valid[kValidWords];
+struct PackTile { // one warp's 32 reads
+    uint64_t off[32];  // first base of the read, relative to the batch
+    uint32_t pre[33];  // units (32 bases) before read i
+    int start[32];
+    uint32_t tlen[32]; // 0 for a read the length rule drops
+    uint32_t flag[32]; // KID_PK_FLAG once a base outside ACGT was seen
 };
 
 // 16 validity bits (first base in bit 15) -> 32-bit mask with both bits of every valid base set
@@ -37,153 +39,126 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v)
     return v | (v << 1);
 }
 
-__device__ __forceinline__ void stage_bases(PackStrip &strip, const uint4 &v, bool accept_u, int lane)
+// 16 bases in four little-endian words -> code word + 16 validity bits (first base on top)
+__device__ __forceinline__ void pack16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, bool accept_u,
+                                       uint32_t &code, uint32_t &v16)
 {
-    const unsigned full = 0xFFFFFFFFu;
-    __syncwarp();
     uint32_t c0, c1, c2, c3, v0, v1, v2, v3;
-    pack4(v.x, accept_u, c0, v0);
-    pack4(v.y, accept_u, c1, v1);
-    pack4(v.z, accept_u, c2, v2);
-    pack4(v.w, accept_u, c3, v3);
-    const uint32_t v16 = (v0 << 12) | (v1 << 8) | (v2 << 4) | v3;
-    strip.codes[lane] = ((c0 << 24) | (c1 << 16) | (c2 << 8) | c3) & spread16(v16); // other bases: code 0
-    const uint32_t nb = __shfl_down_sync(full, v16, 1);
-    if ((lane & 1) == 0) strip.valid[lane >> 1] = (v16 << 16) | nb;
-    __syncwarp();
-}
-
-// words of `n` bases that start at staged index tb: lane k gets code word k (16 bases) and validity
-// word k (32 bases), both cut off after base n
-__device__ __forceinline__ void extract(const PackStrip &strip, int tb, int n, int lane, uint32_t &code, uint32_t &valid)
-{
-    {
-        const int t = tb + 16 * lane, w = t >> 4, sh = (t & 15) * 2, rem = n - 16 * lane;
-        code = 0;
-        if (rem > 0 && w + 1 < kCodeWords) {
-            code = __funnelshift_l(strip.codes[w + 1], strip.codes[w], sh);
-            if (rem < 16) code &= ~0u << (2 * (16 - rem));
-        }
-    }
-    {
-        const int t = tb + 32 * lane, w = t >> 5, sh = t & 31, rem = n - 32 * lane;
-        valid = 0;
-        if (rem > 0 && w + 1 < kValidWords) {
-            valid = __funnelshift_l(strip.valid[w + 1], strip.valid[w], sh);
-            if (rem < 32) valid &= ~0u << (32 - rem);
-        }
-    }
+    pack4(x0, accept_u, c0, v0);
+    pack4(x1, accept_u, c1, v1);
+    pack4(x2, accept_u, c2, v2);
+    pack4(x3, accept_u, c3, v3);
+    code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    v16 = (v0 << 12) | (v1 << 8) | (v2 << 4) | v3;
 }
 
 template <bool HAS_QUAL>
 __global__ void __launch_bounds__(kPackThreads)
 kid_pack_kernel(const KidPackParams p)
 {
-    __shared__ PackStrip strips[kPackThreads / 32];
+    __shared__ PackTile tiles[kPackThreads / 32];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    PackStrip &strip = strips[threadIdx.x >> 5];
-    if (lane < kCodeWords - 32) strip.codes[32 + lane] = 0;
-    if (lane < kValidWords - 16) strip.valid[16 + lane] = 0;
+    PackTile &t = tiles[threadIdx.x >> 5];
 
-    const size_t n_groups = (p.n_reads + kGroup - 1) / kGroup;
+    const size_t n_tiles = (p.n_reads + 31) / 32;
     const size_t warps_total = (size_t)gridDim.x * (kPackThreads / 32);
-    for (size_t grp = (size_t)blockIdx.x * (kPackThreads / 32) + (threadIdx.x >> 5); grp < n_groups; grp += warps_total) {
-        const size_t r0 = grp * kGroup;
-        const int nr = (int)min((size_t)kGroup, p.n_reads - r0);
-        const uint64_t g0 = __ldg(p.off + r0) - p.off_bias;
-        int rel[kGroup + 1]; // saturated: anything beyond the window only has to fail the test below
-        rel[0] = 0;
-#pragma unroll
-        for (int i = 1; i <= kGroup; i++) {
-            const uint64_t d = i <= nr ? __ldg(p.off + r0 + i) - p.off_bias - g0 : (uint64_t)rel[i - 1];
-            rel[i] = d > 0x7FFFFFFFull ? 0x7FFFFFFF : (int)d;
+    for (size_t tile = (size_t)blockIdx.x * (kPackThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+        const size_t r = tile * 32 + (size_t)lane;
+        const bool have = r < p.n_reads;
+        uint64_t o = 0;
+        int len = 0;
+        if (have) {
+            o = __ldg(p.off + r) - p.off_bias;
+            const uint64_t l64 = __ldg(p.off + r + 1) - p.off_bias - o;
+            len = l64 > 0x7FFFFFFFull ? 0x7FFFFFFF : (int)l64; // one read < 2^31 bases
         }
-        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(p.seq) + g0;
-        const uintptr_t abase = addr0 & ~(uintptr_t)15;
-        const int delta = (int)(addr0 - abase);
-
-        if (rel[kGroup] <= kGroupMaxSpan - delta) {
-            // ---- grouped path: one load / pack for all reads of the group
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (16 * lane < delta + rel[kGroup]) v = load_stream16(reinterpret_cast<const uint4 *>(abase) + lane);
-            int st[kGroup], sp[kGroup];
-            if (HAS_QUAL) {
-                const signed char *q = reinterpret_cast<const signed char *>(p.qual) + g0;
-                int qa[kGroup], qb[kGroup];
-#pragma unroll
-                for (int i = 0; i < kGroup; i++) { // all quality loads in flight before any is used
-                    const int len = rel[i + 1] - rel[i];
-                    qa[i] = lane < len ? (int)q[rel[i] + lane] : -128;
-                    qb[i] = lane < len ? (int)q[rel[i + 1] - 1 - lane] : -128;
-                }
-#pragma unroll
-                for (int i = 0; i < kGroup; i++) trim_read(q + rel[i], rel[i + 1] - rel[i], qa[i], qb[i], lane, st[i], sp[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < kGroup; i++) { st[i] = 0; sp[i] = rel[i + 1] - rel[i] - 1; }
+        // ---- TRIM (:724-753)
+        int start = 0, stop = len - 1;
+        if (HAS_QUAL) {
+            const signed char *q = reinterpret_cast<const signed char *>(p.qual) + o;
+            bool slow = have && len > 0;
+            if (have && len >= 6) {
+                const int a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
+                const int b0 = q[len - 1], b1 = q[len - 2], b2 = q[len - 3], b3 = q[len - 4];
+                // both end bases and both end windows pass: nothing to trim
+                slow = !(a0 >= 49 && b0 >= 49 && a0 + a1 + a2 + a3 - 128 >= 68 && b0 + b1 + b2 + b3 - 128 >= 68);
             }
-            stage_bases(strip, v, p.accept_u, lane);
-#pragma unroll
-            for (int i = 0; i < kGroup; i++) {
-                if (i >= nr) break;
-                const size_t r = r0 + i;
-                const int tl = sp[i] - st[i] + 1;
-                const bool kept = tl > KID_KSIZE; // :755
-                const uint32_t wf = (uint32_t)kid_pack_word_index(g0 + (uint64_t)rel[i], r);
-                uint32_t flag = 0;
-                if (kept) {
-                    uint32_t code, valid;
-                    extract(strip, delta + rel[i] + st[i], tl, lane, code, valid);
-                    const int cwn = (tl + 15) >> 4, vwn = (tl + 31) >> 5;
-                    const int rem = tl - 32 * lane;
-                    const uint32_t want = rem >= 32 ? ~0u : (rem > 0 ? ~0u << (32 - rem) : 0u);
-                    flag = __any_sync(full, valid != want) ? KID_PK_FLAG : 0u;
-                    if (lane < cwn) p.words[wf + lane] = code;
-                    if (flag && lane < vwn) p.words[wf + cwn + lane] = valid;
-                }
-                if (lane == 0) {
-                    p.meta[r] = make_uint2(wf | flag, kept ? (uint32_t)tl : 0u);
-                    if (p.out_span) { p.out_span[2 * r] = (uint32_t)st[i]; p.out_span[2 * r + 1] = (uint32_t)sp[i]; }
-                }
+            unsigned todo = __ballot_sync(full, slow);
+            while (todo) { // the warp-cooperative search, one read after the other
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint64_t oi = __shfl_sync(full, o, i);
+                const int li = __shfl_sync(full, len, i);
+                const signed char *qi = reinterpret_cast<const signed char *>(p.qual) + oi;
+                const int qa = lane < li ? (int)qi[lane] : -128;
+                const int qb = lane < li ? (int)qi[li - 1 - lane] : -128;
+                int st, sp;
+                trim_read(qi, li, qa, qb, lane, st, sp);
+                if (lane == i) { start = st; stop = sp; }
             }
-            continue;
         }
-
-        // ---- one read at a time (long reads): windows of kLongStep bases from the trimmed start
-        for (int i = 0; i < nr; i++) {
-            const size_t r = r0 + i;
-            const uint64_t gi = __ldg(p.off + r) - p.off_bias;
-            const int len = (int)(__ldg(p.off + r + 1) - p.off_bias - gi);
-            int start = 0, stop = len - 1;
-            if (HAS_QUAL && len > 0) {
-                const signed char *q = reinterpret_cast<const signed char *>(p.qual) + gi;
-                const int qa = lane < len ? (int)q[lane] : -128;
-                const int qb = lane < len ? (int)q[len - 1 - lane] : -128;
-                trim_read(q, len, qa, qb, lane, start, stop);
+        const int tl = stop - start + 1;
+        const bool kept = have && tl > KID_KSIZE; // :755
+        const uint32_t units = kept ? ((uint32_t)tl + 31u) >> 5 : 0u;
+        uint32_t incl = units; // inclusive prefix sum over the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += v;
+        }
+        __syncwarp();
+        t.off[lane] = o;
+        t.start[lane] = start;
+        t.tlen[lane] = kept ? (uint32_t)tl : 0u;
+        t.flag[lane] = 0;
+        t.pre[lane + 1] = incl;
+        if (lane == 0) t.pre[0] = 0;
+        __syncwarp();
+        const uint32_t total = t.pre[32];
+        // ---- PACK: one lane per unit of 32 bases
+        for (uint32_t w = lane; w < total; w += 32) {
+            int ri = 0; // the read this unit belongs to: the last one with pre[ri] <= w
+#pragma unroll
+            for (int step = 16; step; step >>= 1)
+                if (t.pre[ri + step] <= w) ri += step;
+            const uint32_t u = w - t.pre[ri];
+            const uint32_t tlr = t.tlen[ri];
+            const int nb = min(32, (int)(tlr - 32u * u)); // bases of this unit, >= 1
+            const uint64_t ro = t.off[ri];
+            const uintptr_t src = reinterpret_cast<uintptr_t>(p.seq) + ro + (uint64_t)t.start[ri] + 32ull * u;
+            const uint32_t *al = reinterpret_cast<const uint32_t *>(src & ~(uintptr_t)3);
+            const int bsh = (int)(src & 3) * 8;
+            const int last_word = (int)(((src & 3) + (uintptr_t)nb - 1) >> 2); // aligned words that hold a needed byte: 0..last_word
+            uint32_t a[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) a[k] = k <= last_word ? __ldg(al + k) : 0u;
+            uint32_t x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = __funnelshift_r(a[k], a[k + 1], bsh);
+            uint32_t c0, c1, v0, v1;
+            pack16(x[0], x[1], x[2], x[3], p.accept_u, c0, v0);
+            pack16(x[4], x[5], x[6], x[7], p.accept_u, c1, v1);
+            uint32_t valid = (v0 << 16) | v1;
+            const uint32_t want = nb >= 32 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (32 - nb);
+            valid &= want; // bytes behind the read's last base are not part of it
+            if (valid != want) {
+                c0 &= spread16(valid >> 16); // other bases: code 0
+                c1 &= spread16(valid & 0xFFFFu);
+                atomicOr(&t.flag[ri], KID_PK_FLAG);
             }
-            const int tl = stop - start + 1;
-            const bool kept = tl > KID_KSIZE;
-            const uint32_t wf = (uint32_t)kid_pack_word_index(gi, r);
-            if (kept) {
-                const int cwn = (tl + 15) >> 4;
-                for (int wb = 0; wb < tl; wb += kLongStep) {
-                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.seq) + gi + (uint64_t)start + (uint64_t)wb;
-                    const uintptr_t ab = a0 & ~(uintptr_t)15;
-                    const int dl = (int)(a0 - ab), nb = min(kLongStep, tl - wb);
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (16 * lane < dl + nb) v = load_stream16(reinterpret_cast<const uint4 *>(ab) + lane);
-                    stage_bases(strip, v, p.accept_u, lane);
-                    uint32_t code, valid;
-                    extract(strip, dl, nb, lane, code, valid);
-                    if (16 * lane < nb) p.words[wf + (wb >> 4) + lane] = code;
-                    if (32 * lane < nb) p.words[wf + cwn + (wb >> 5) + lane] = valid;
-                }
-            }
-            if (lane == 0) {
-                p.meta[r] = make_uint2(wf | (kept ? KID_PK_FLAG : 0u), kept ? (uint32_t)tl : 0u);
-                if (p.out_span) { p.out_span[2 * r] = (uint32_t)start; p.out_span[2 * r + 1] = (uint32_t)stop; }
-            }
+            if (nb < 16) c0 &= 0xFFFFFFFFu << (2 * (16 - nb));
+            if (nb < 32) c1 = nb > 16 ? c1 & (0xFFFFFFFFu << (2 * (32 - nb))) : 0u;
+            const uint32_t wf = (uint32_t)kid_pack_word_index(ro, tile * 32 + (size_t)ri);
+            const uint32_t cwn = (tlr + 15u) >> 4;
+            p.words[wf + 2 * u] = c0;
+            if (2 * u + 1 < cwn) p.words[wf + 2 * u + 1] = c1;
+            p.words[wf + cwn + u] = valid; // always written (the layout reserves the room); read only if flagged
+        }
+        __syncwarp();
+        if (have) {
+            p.meta[r] = make_uint2((uint32_t)kid_pack_word_index(o, r) | t.flag[lane], t.tlen[lane]);
+            if (p.out_span) { p.out_span[2 * r] = (uint32_t)start; p.out_span[2 * r + 1] = (uint32_t)stop; }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -197,7 +172,7 @@ kid_pack_kernel(const KidPackParams p)
 cudaError_t kid_launch_pack(const KidPackParams &p, int sm_count, cudaStream_t stream)
 {
     if (p.n_reads == 0) return cudaSuccess;
-    const size_t warps = (p.n_reads + kGroup - 1) / kGroup;
+    const size_t warps = (p.n_reads + 31) / 32;
     size_t blocks = (warps + kPackThreads / 32 - 1) / (kPackThreads / 32);
     const size_t cap = (size_t)sm_count * 8; // 2048 threads per SM: 8 resident blocks, grid-stride beyond
     if (blocks > cap) blocks = cap;

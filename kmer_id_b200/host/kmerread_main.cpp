@@ -10,6 +10,7 @@
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
 #include "device_warmup.hpp"
+#include "batch_pipeline.hpp"
 #include "read_reader.hpp"
 
 #include <cstdio>
@@ -39,21 +40,10 @@ long long g_tct = 0;
 void run_file(kid_sample *smp, ReadFormat fmt, const std::string &path)
 {
     if (fmt == ReadFormat::GzFasta) std::cout << "true" << std::endl; // process_fagz :789
-    ReadBatchReader reader(fmt, path, (size_t)1 << 19, (size_t)96 << 20);
-    std::vector<int32_t> taxon;
-    for (;;) {
-        ReadBatch *b = reader.next();
-        if (b->n) {
-            taxon.resize(b->n);
-            if (kid_classify_host(smp, b->seq, b->has_qual ? b->qual : nullptr, b->off.data(), b->n, taxon.data(),
-                                  nullptr) != 0)
-                die(1, kid_last_error());
-            for (size_t r = 0; r < b->n; r++) g_tct += taxon[r] >= 0; // tct++ per processed read (:624)
-        }
-        const bool last = b->last;
-        reader.recycle(b);
-        if (last) break;
-    }
+    ReadBatchReader reader(fmt, path, (size_t)1 << 19, (size_t)96 << 20, pipeline_batches());
+    classify_stream(smp, reader, [&](const ReadBatch &b) {
+        for (size_t r = 0; r < b.n; r++) g_tct += b.taxon[r] >= 0; // tct++ per processed read (:624)
+    });
     if (fmt == ReadFormat::PlainFasta && reader.open_failed()) std::cout << "nark " << path << std::endl; // :969-971
 }
 

@@ -10,6 +10,7 @@
 #include "../../include/kmer_id.h"
 #include "db_loader.hpp"
 #include "device_warmup.hpp"
+#include "batch_pipeline.hpp"
 #include "read_reader.hpp"
 
 #include <cstdio>
@@ -45,39 +46,26 @@ struct JobState {
 
 void run_file(kid_sample *smp, ReadFormat fmt, const std::string &path, JobState &st)
 {
-    ReadBatchReader reader(fmt, path, (size_t)1 << 19, (size_t)96 << 20);
-    std::vector<int32_t> taxon;
-    std::vector<uint32_t> span;
-    for (;;) {
-        ReadBatch *b = reader.next();
-        if (b->n) {
-            taxon.resize(b->n);
-            span.resize(2 * b->n);
-            if (kid_classify_host(smp, b->seq, b->has_qual ? b->qual : nullptr, b->off.data(), b->n, taxon.data(),
-                                  span.data()) != 0)
-                die(1, kid_last_error());
-            for (size_t r = 0; r < b->n; r++) { // process_read :613-623, in stream order
-                const int fin = taxon[r];
-                if (fin < 0) continue;
-                const bool first12 = fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM && st.save_target == 0;
-                const bool wanted = fin > 1 && fin == st.save_target;
-                for (int k = 0; k < 2; k++) {
-                    if (!(k == 0 ? first12 : wanted)) continue;
-                    std::ofstream &o = k == 0 ? st.outread1 : st.outread2;
-                    o << ">" << fin << ":";
-                    o.write(b->names.data() + b->name_off[r], b->name_off[r + 1] - b->name_off[r]);
-                    o << std::endl;
-                    o.write((const char *)b->seq + b->off[r] + span[2 * r], span[2 * r + 1] - span[2 * r] + 1);
-                    o << std::endl;
-                }
-                st.gcount_host[(size_t)fin]++;
-                st.tct++;
+    ReadBatchReader reader(fmt, path, (size_t)1 << 19, (size_t)96 << 20, pipeline_batches(), 0, BatchMode::Packed, KID_DB_ACCEPT_U);
+    classify_stream(smp, reader, [&](const ReadBatch &b) {
+        for (size_t r = 0; r < b.n; r++) { // process_read :613-623, in stream order
+            const int fin = b.taxon[r];
+            if (fin < 0) continue;
+            const bool first12 = fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM && st.save_target == 0;
+            const bool wanted = fin > 1 && fin == st.save_target;
+            for (int k = 0; k < 2; k++) {
+                if (!(k == 0 ? first12 : wanted)) continue;
+                std::ofstream &o = k == 0 ? st.outread1 : st.outread2;
+                o << ">" << fin << ":";
+                o.write(b.names.data() + b.name_off[r], b.name_off[r + 1] - b.name_off[r]);
+                o << std::endl;
+                o.write((const char *)b.seq + b.off[r] + b.span[2 * r], b.span[2 * r + 1] - b.span[2 * r] + 1);
+                o << std::endl;
             }
+            st.gcount_host[(size_t)fin]++;
+            st.tct++;
         }
-        const bool last = b->last;
-        reader.recycle(b);
-        if (last) break;
-    }
+    });
     if (fmt == ReadFormat::PlainFasta && reader.open_failed()) std::cout << "nark " << path << std::endl;
 }
 } // namespace

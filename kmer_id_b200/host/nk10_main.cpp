@@ -10,6 +10,7 @@
 // timings to stderr, and the parsed probe list is cached next to probes10.txt.gz as
 // probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
 #include "../../include/kmer_id.h"
+#include "batch_pipeline.hpp"
 #include "db_loader.hpp"
 #include "device_warmup.hpp"
 #include "pgz.hpp"
@@ -48,7 +49,7 @@ double now()
     exit(code);
 }
 
-constexpr size_t kBatchBytes = (size_t)48 << 20; // bases per batch handed to kid_classify_host
+constexpr size_t kBatchBytes = (size_t)48 << 20; // bases per batch (one asynchronous submission)
 
 struct SampleState {
     std::vector<int> gcount_host; // running copy, only to decide the first SAVENUM reads per taxon
@@ -68,47 +69,35 @@ void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::of
               std::vector<SavedRead> *saved)
 {
     // R1 and R2 are inflated at the same time unless KID_SERIAL is set: share the cores
-    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, 3,
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, pipeline_batches(),
                            default_gz_threads(getenv("KID_SERIAL") ? 1 : 2));
-    std::vector<int32_t> taxon;
-    std::vector<uint32_t> span;
-    for (;;) {
-        ReadBatch *b = reader.next();
-        if (b->n) {
-            taxon.resize(b->n);
-            span.resize(2 * b->n);
-            if (kid_classify_host(smp, b->seq, b->qual, b->off.data(), b->n, taxon.data(), span.data()) != 0)
-                die(1, kid_last_error());
-            for (size_t r = 0; r < b->n; r++) {
-                const int fin = taxon[r];
-                if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
-                if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) {
-                    const char *name = b->names.data() + b->name_off[r];
-                    const size_t nlen = b->name_off[r + 1] - b->name_off[r];
-                    const char *bases = (const char *)b->seq + b->off[r] + span[2 * r];
-                    const size_t blen = span[2 * r + 1] - span[2 * r] + 1;
-                    if (outread) {
-                        *outread << ">" << fin << ":";
-                        outread->write(name, (std::streamsize)nlen);
-                        *outread << std::endl;
-                        outread->write(bases, (std::streamsize)blen);
-                        *outread << std::endl;
-                    } else if (saved) {
-                        SavedRead sr;
-                        sr.taxon = fin;
-                        sr.text = ">" + std::to_string(fin) + ":" + std::string(name, nlen) + "\n" +
-                                  std::string(bases, blen) + "\n";
-                        saved->push_back(std::move(sr));
-                    }
+    classify_stream(smp, reader, [&](const ReadBatch &b) {
+        for (size_t r = 0; r < b.n; r++) {
+            const int fin = b.taxon[r];
+            if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
+            if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) {
+                const char *name = b.names.data() + b.name_off[r];
+                const size_t nlen = b.name_off[r + 1] - b.name_off[r];
+                const char *bases = (const char *)b.seq + b.off[r] + b.span[2 * r];
+                const size_t blen = b.span[2 * r + 1] - b.span[2 * r] + 1;
+                if (outread) {
+                    *outread << ">" << fin << ":";
+                    outread->write(name, (std::streamsize)nlen);
+                    *outread << std::endl;
+                    outread->write(bases, (std::streamsize)blen);
+                    *outread << std::endl;
+                } else if (saved) {
+                    SavedRead sr;
+                    sr.taxon = fin;
+                    sr.text = ">" + std::to_string(fin) + ":" + std::string(name, nlen) + "\n" +
+                              std::string(bases, blen) + "\n";
+                    saved->push_back(std::move(sr));
                 }
-                st.gcount_host[(size_t)fin]++;
-                st.tct++;
             }
+            st.gcount_host[(size_t)fin]++;
+            st.tct++;
         }
-        const bool last = b->last;
-        reader.recycle(b);
-        if (last) break;
-    }
+    });
 }
 } // namespace
 

@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -19,31 +20,49 @@ namespace kidhost {
 
 enum class ReadFormat { GzFastq, PlainFastq, GzFasta, PlainFasta };
 
-// Pinned host buffers sized once; reads are concatenated with no separators.
+// What a batch carries for the GPU.
+//   Packed (the hosts): every record is trimmed and 2-bit packed by kid_pack_reads while its lines are
+//           still in cache; words/meta/taxon are pinned and go to kid_classify_packed_async as they
+//           are.  Qualities are never copied; the bases are kept in ordinary memory for _reads.txt.
+//   Text    (tests, and callers of kid_classify_host): bases and qualities in pinned buffers.
+enum class BatchMode { Packed, Text };
+
+// Buffers sized once; reads are concatenated with no separators.
 struct ReadBatch {
-    uint8_t *seq = nullptr;   // pinned, cap_bytes + 16
-    uint8_t *qual = nullptr;  // pinned, same offsets as seq (only the first seqlen bytes of a
-                              // quality line are ever looked at, :724-753); unused for FASTA
+    uint8_t *seq = nullptr;   // cap_bytes + 16 (pinned in Text mode)
+    uint8_t *qual = nullptr;  // Text mode, FASTQ: pinned, same offsets as seq (only the first seqlen
+                              // bytes of a quality line are ever looked at, :724-753)
+    uint32_t *words = nullptr; // Packed mode: pinned, n_words used of cap_words (include/kmer_id.h)
+    uint32_t *meta = nullptr;  // Packed mode: pinned, 2 * (n + 1) used
+    int32_t *taxon = nullptr;  // Packed mode: pinned, cap_reads: where the GPU's per-read result lands
+    std::vector<uint32_t> span;     // Packed mode: 2n, (start, stop) as process_qual leaves them
     std::vector<uint64_t> off;      // n + 1
     std::vector<char> names;        // header lines as the reference keeps them, concatenated
     std::vector<uint32_t> name_off; // n + 1
-    size_t n = 0;
-    size_t cap_bytes = 0;
+    size_t n = 0, n_words = 0;
+    size_t cap_bytes = 0, cap_words = 0, cap_reads = 0;
     bool has_qual = true;
     bool last = false;        // no more batches after this one
+    int slot = -1;            // for the consumer: the asynchronous slot this batch was submitted on
 };
 
-// Page-locks the buffers that `readers` ReadBatchReaders of this max_bytes/depth will ask for and
-// parks them in the process-wide pool (read_reader.cpp); meant for a helper thread at start-up.
-void prewarm_batch_buffers(size_t max_bytes, int readers, bool with_quality, int depth = 3);
+// Page-locks the buffers that `readers` ReadBatchReaders of this shape will ask for and parks them in
+// the process-wide pool (read_reader.cpp); meant for a helper thread at start-up.
+void prewarm_batch_buffers(size_t max_reads, size_t max_bytes, int readers, int depth = 4);
+
+// batches a reader needs so that `slots` submissions can be in flight while its parse workers stay busy
+int pipeline_depth(int slots);
 
 class ReadBatchReader {
 public:
     // starts a background thread that inflates/parses `path` into batches of at most max_reads
     // reads / max_bytes bases, keeping at most `depth` batches ahead of the consumer
-    // gz_threads: inflate workers for gz inputs (0 = default_gz_threads() of pgz.hpp)
+    // gz_threads: inflate workers for gz inputs (0 = default_gz_threads() of pgz.hpp).  Packed gz FASTQ
+    // is parsed, trimmed and packed by several threads (KID_PARSE_THREADS, default 3; 0 = on the reader
+    // thread itself): `depth` must then cover them (pipeline_depth()).
+    // pack_flags: KID_DB_ACCEPT_U or 0 (Packed mode)
     ReadBatchReader(ReadFormat fmt, const std::string &path, size_t max_reads, size_t max_bytes, int depth = 3,
-                    unsigned gz_threads = 0);
+                    unsigned gz_threads = 0, BatchMode mode = BatchMode::Packed, unsigned pack_flags = 0);
     ~ReadBatchReader();
     ReadBatch *next();          // blocks; the batch flagged `last` ends the stream
     void recycle(ReadBatch *b);
@@ -56,18 +75,28 @@ private:
     void run_gz_fasta(const std::string &path);
     void run_plain_fasta(const std::string &path);
     void emit(const char *acc, size_t acclen, const char *seq, size_t seqlen, const char *qual);
+    void emit_into(ReadBatch &b, const char *acc, size_t acclen, const char *seq, size_t seqlen, const char *qual);
     ReadBatch *get_free();
     void publish(ReadBatch *b);
+    void alloc_batch(ReadBatch &b, size_t cap_bytes, size_t cap_reads);
+    void free_batch(ReadBatch &b);
+    void run_gz_fastq_parallel(const std::string &path);
+    void publish_ordered(uint64_t index, ReadBatch *b);
 
     ReadFormat fmt_;
     size_t max_reads_, max_bytes_;
     unsigned gz_threads_ = 0;
+    BatchMode mode_ = BatchMode::Packed;
+    unsigned pack_flags_ = 0;
     std::vector<std::unique_ptr<ReadBatch>> pool_;
     std::deque<ReadBatch *> free_, ready_;
     std::mutex mu_;
     std::condition_variable cv_;
     std::thread th_;
     ReadBatch *cur_ = nullptr;
+    std::map<uint64_t, ReadBatch *> done_; // parallel gz FASTQ: finished batches waiting for their turn
+    uint64_t next_pub_ = 0;
+    unsigned parse_threads_ = 0;
     bool finished_ = false;
     bool open_failed_ = false;
 };

@@ -3,6 +3,8 @@
 // three malloc-backed stubs below).
 //   host_dump probes <probes.gz> <signed 0|1> <cap_log2_cells or 0>   -> "lines N\n" then "key taxon" per entry
 //   host_dump reads  <gzfastq|fastq|gzfasta|fasta> <file>             -> one record per line: acc \t seq \t qual
+//   host_dump packed <gzfastq|fastq|gzfasta|fasta> <file> <flags>     -> per record: acc \t start \t stop \t tlen \t flagged \t decoded
+//                                                                       bases (non-ACGT as N), from the reader's packed batches
 //   host_dump tree   <tree file> <n_taxa>                             -> parent[] one per line, or "ERR msg"
 #include "../../include/kmer_id.h"
 #include "../../kmer_id_b200/host/db_loader.hpp"
@@ -41,7 +43,7 @@ int main(int argc, char **argv)
         const std::string k = argv[2];
         const ReadFormat fmt = k == "gzfastq" ? ReadFormat::GzFastq : k == "fastq" ? ReadFormat::PlainFastq
                              : k == "gzfasta" ? ReadFormat::GzFasta : ReadFormat::PlainFasta;
-        ReadBatchReader reader(fmt, argv[3], 7, 4096, 2); // tiny batches: exercise the batch boundaries
+        ReadBatchReader reader(fmt, argv[3], 7, 4096, 2, 0, BatchMode::Text); // tiny batches: exercise the batch boundaries
         for (;;) {
             ReadBatch *b = reader.next();
             for (size_t r = 0; r < b->n; r++) {
@@ -59,6 +61,32 @@ int main(int argc, char **argv)
         if (reader.open_failed()) printf("OPEN_FAILED\n");
         return 0;
     }
+    if (cmd == "packed") {
+        const std::string k = argv[2];
+        const ReadFormat fmt = k == "gzfastq" ? ReadFormat::GzFastq : k == "fastq" ? ReadFormat::PlainFastq
+                             : k == "gzfasta" ? ReadFormat::GzFasta : ReadFormat::PlainFasta;
+        ReadBatchReader reader(fmt, argv[3], 7, 4096, 2, 0, BatchMode::Packed, argc > 4 ? (unsigned)atoi(argv[4]) : 0u);
+        for (;;) {
+            ReadBatch *b = reader.next();
+            if (b->n && (b->meta[2 * b->n] & 0x7FFFFFFFu) != b->n_words) { printf("BAD_END\n"); return 1; }
+            for (size_t r = 0; r < b->n; r++) {
+                fwrite(b->names.data() + b->name_off[r], 1, b->name_off[r + 1] - b->name_off[r], stdout);
+                const uint32_t w0 = b->meta[2 * r] & 0x7FFFFFFFu, flagged = b->meta[2 * r] >> 31, tlen = b->meta[2 * r + 1];
+                printf("\t%d\t%d\t%u\t%u\t", (int)b->span[2 * r], (int)b->span[2 * r + 1], tlen, flagged);
+                const uint32_t cw = (tlen + 15) / 16;
+                for (uint32_t i = 0; i < tlen; i++) {
+                    const uint32_t c = (b->words[w0 + i / 16] >> (30 - 2 * (i % 16))) & 3u;
+                    const uint32_t v = flagged ? (b->words[w0 + cw + i / 32] >> (31 - i % 32)) & 1u : 1u;
+                    fputc(v ? "ACGT"[c] : 'N', stdout);
+                }
+                fputc('\n', stdout);
+            }
+            const bool last = b->last;
+            reader.recycle(b);
+            if (last) break;
+        }
+        return 0;
+    }
     if (cmd == "loadtime") { // <probes.gz> <threads>: timing only
         ProbeSet ps;
         const auto t0 = std::chrono::steady_clock::now();
@@ -74,7 +102,9 @@ int main(int argc, char **argv)
     if (cmd == "readtime") { // <gz fastq>: timing only; the second pass runs on recycled (already touched) buffers
         for (int pass = 0; pass < 2; pass++) {
             const auto t0 = std::chrono::steady_clock::now();
-            ReadBatchReader reader(ReadFormat::GzFastq, argv[2], 1u << 18, 48u << 20, 3);
+            const bool packed = argc > 3 && atoi(argv[3]) != 0; // the hosts' path: trim + pack on the parse workers
+            ReadBatchReader reader(ReadFormat::GzFastq, argv[2], 1u << 18, 48u << 20, packed ? pipeline_depth(2) : 3, 0,
+                                   packed ? BatchMode::Packed : BatchMode::Text);
             size_t n = 0, bytes = 0;
             for (;;) {
                 ReadBatch *b = reader.next();

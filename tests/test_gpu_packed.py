@@ -72,7 +72,7 @@ def test_device_packer_equals_host_packer(seed, n, kw):
         gt, gf, gc, gv, gp, _ = unpack(gw, gm, r)
         assert gt == ht and gp, r
         # the device packer also flags every read that takes its one-at-a-time path; never fewer
-        assert gf or not hf, r
+        assert gf == hf, r
         assert np.array_equal(gc, hc) and np.array_equal(gv, hv), r
         w0 = int(gm[2 * r]) & 0x7FFFFFFF
         rel = int(batch.off[r])

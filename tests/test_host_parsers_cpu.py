@@ -237,3 +237,53 @@ def test_tree_loader_rules(tmp_path):
     open(p, "wb").write(b"2 30\n")
     assert _dump("tree", p, 10).stdout.startswith(b"ERR")
     assert [int(x) for x in _dump("tree", os.path.join(str(tmp_path), "none.txt"), 5).stdout.split()] == [1] * 5
+
+
+def test_reader_packed_batches_match_text_batches_and_oracle_trim(tmp_path):
+    """The hosts' batches (BatchMode::Packed: trimmed, 2-bit packed by kid_pack_reads per record) carry
+    exactly what the text batches + process_qual would give, across batch boundaries (7 reads / 4 KiB
+    per batch) and for a FASTA record that is longer than a whole batch."""
+    rng = np.random.default_rng(94)
+    db = H.make_db(rng, 50)
+    batch = H.make_reads(rng, db, 80, ragged=True, n_rate=0.01, lower_rate=0.05)
+    d = str(tmp_path)
+    fq = b""
+    for r in range(batch.n):
+        a, b = int(batch.off[r]), int(batch.off[r + 1])
+        q = bytes(c if c not in (9, 10, 11, 12, 13, 32) else 73 for c in batch.qual[a:b].tobytes())
+        # CRLF, blank and "\r"-only lines in odd places (they do not advance the 4-line state), quality
+        # lines longer than their read
+        eol = b"\r\n" if r % 3 == 0 else b"\n"
+        fq += b"@r%d" % r + eol + (b"\n" if r % 5 == 0 else b"") + batch.seq[a:b].tobytes() + eol + (b"\r\n" if r % 4 == 1 else b"")
+        fq += b"+" + eol + q + (b"IIII" if r % 7 == 0 else b"") + eol + (b"\n\n" if r % 11 == 0 else b"")
+    fq += b"@dropped no final newline\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII"
+    with gzip.open(os.path.join(d, "p.fastq.gz"), "wb") as f:
+        f.write(fq)
+    text = _records("gzfastq", os.path.join(d, "p.fastq.gz"))
+    r = _dump("packed", "gzfastq", os.path.join(d, "p.fastq.gz"), 0)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(b"\t") for l in r.stdout.split(b"\n") if l]
+    assert len(rows) == len(text) == batch.n
+    lut = np.full(256, ord("N"), np.uint8)
+    for ch in b"ACGT":
+        lut[ch] = ch
+        lut[ch | 0x20] = ch
+    for (acc, seq, qual), row in zip(text, rows):
+        st, sp = kor.trim(qual, len(seq))
+        assert row[0] == acc and (int(row[1]), int(row[2])) == (st, sp)
+        if sp - st < 30:
+            assert int(row[3]) == 0 and (len(row) < 6 or row[5] == b"")
+            continue
+        want = lut[np.frombuffer(seq[st:sp + 1], np.uint8)].tobytes()
+        assert int(row[3]) == sp - st + 1 and row[5] == want
+        assert int(row[4]) == int(b"N" in want)
+    # FASTA through the same path: whole records, U accepted with flag 1
+    big = H._BASES[rng.integers(0, 4, size=30000)].tobytes()  # > 4096 + 16384 bytes: the batch buffer grows for it
+    fa = b">x\n" + b"ACGU" * 20 + b"\n>y\nACGTNNACGT" + b"ACGT" * 10 + b"\n>big\n"
+    fa += b"".join(big[j:j + 60] + b"\n" for j in range(0, len(big), 60)) + b">z\n" + b"ACGT" * 10 + b"\n"
+    open(os.path.join(d, "p.fasta"), "wb").write(fa)
+    r0 = [l.split(b"\t") for l in _dump("packed", "fasta", os.path.join(d, "p.fasta"), 0).stdout.split(b"\n") if l]
+    r1 = [l.split(b"\t") for l in _dump("packed", "fasta", os.path.join(d, "p.fasta"), 1).stdout.split(b"\n") if l]
+    assert r0[0][5] == b"ACGN" * 20 and r1[0][5] == b"ACGT" * 20 and r0[1][5] == b"ACGTNNACGT" + b"ACGT" * 10
+    assert (int(r0[0][4]), int(r1[0][4]), int(r0[1][4])) == (1, 0, 1)
+    assert r0[2][0] == b"big" and r0[2][5] == big and int(r0[2][3]) == 30000 and r0[3][5] == b"ACGT" * 10
