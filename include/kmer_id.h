@@ -13,7 +13,9 @@
  *   - "device pointer" arguments are CUDA global-memory addresses on the db's device.
  *   - there is NO CPU fallback: without a usable CUDA device every call fails with KID_ECUDA.
  *   - a kid_db is immutable after build and may be shared by several kid_sample objects; a
- *     kid_sample is used from one host thread at a time.
+ *     kid_sample is used from one host thread at a time, except that different threads may drive
+ *     DIFFERENT asynchronous slots of one sample at once (R1 and R2 of a sample: kid_classify_*_async
+ *     and kid_wait only; begin / counts need all of them quiet).
  *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream).
  */
 #ifndef KMER_ID_H
@@ -70,7 +72,11 @@ void kid_host_free(void *p);
  *   parent[t]         t = 0..n_taxa-1: Tree1::parent after all add_edge calls (default 1, :103).
  *   keys_on_device    non-zero if keys/taxa are device pointers (then they are read in place).
  *   log2_sectors      0 = size the table from n_keys; else log2 of the number of 32-byte sectors
- *                     (layout M: 12..32, layout K: 22..32).
+ *                     (layout M: 12..32, layout K: 22..32).  The default is a function of n_keys
+ *                     alone (<= 0.225 keys per 3-entry sector: 16 GiB for 1.09e8 keys; KID_DB_DENSE=1
+ *                     halves that for ~3 % fewer lookups/s); it shrinks, with a message on stderr,
+ *                     only when the device cannot hold it.
+ *   n_keys            at most 2^32-2 entries (owner indices are 32-bit during the build).
  * Environment (tuning/test knob): KID_DB_SUB_BITS=2|3|4 forces how many sectors (4, 8, 16) one
  * minimizer addresses in layout M; by default 4, and 8 or 16 only for databases beyond 4e8 keys
  * that device memory keeps densely packed (kid_table2.cuh).
@@ -225,6 +231,25 @@ int kid_seen_or_device(const kid_db *db, uint32_t *dst, const uint32_t *const *s
  * histogram are one kernel and no bitmap is copied or written.  n_src <= 16. */
 int kid_ucount_or_range_device(const kid_db *db, const uint32_t *const *seen_srcs, int n_src,
                                uint64_t word0, uint64_t n_words, int32_t *ucount_partial, void *stream);
+/* ---- one host process, several GPUs (the C++ hosts; no torch, no IPC) ---------------------------
+ * Reads of ONE sample may be dealt to kid_sample objects on different GPUs, each over its own replica
+ * of the same database (kid_db_build is deterministic: replicas agree slot for slot).  Sample end:
+ *   1. kid_device_sync every GPU (all seen bits written);
+ *   2. on GPU r: kid_sample_ucount_partial(shard[r], shards, n, r, n) - ONE kernel that reads word
+ *      range r of every shard's seen bitmap IN PLACE over NVLink (peer access, kid_peer_enable), ORs
+ *      them and histograms the result into that shard's ucount buffer (zeroed first);
+ *   3. sum gcount and the partial ucounts over the GPUs: ncclAllReduce in place on the device buffers
+ *      (kid_sample_gcount_device / kid_sample_ucount_device), or read them back and add;
+ *   4. kid_sample_read_counts on any shard.
+ * kmer_id_b200/host/multi_gpu.hpp does exactly this. */
+/* peer access between every ordered pair of the listed devices (idempotent) */
+int kid_peer_enable(const int *devices, int n);
+int kid_sample_ucount_partial(kid_sample *s, kid_sample *const *shards, int n_shards, int part, int n_parts,
+                              void *stream);
+int kid_sample_ucount_device(kid_sample *s, int32_t **ucount);
+/* plain device -> host copies of the sample's gcount / ucount buffers as they are (no histogram pass) */
+int kid_sample_read_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *stream);
+int kid_device_sync(int device);
 /* Make the sample keep its seen flags in caller-owned device memory of at least n_words 32-bit
  * words (e.g. a symmetric-memory allocation that peers can map).  The buffer is cleared by
  * kid_sample_begin like the internal one and is not freed by the library. */

@@ -71,6 +71,11 @@ _SIGS = {
     "kid_seen_or_device": (_i, [_vp, _vp, C.POINTER(_vp), _i, _u64, _u64, _vp]),
     "kid_ucount_or_range_device": (_i, [_vp, C.POINTER(_vp), _i, _u64, _u64, _vp, _vp]),
     "kid_sample_use_seen_buffer": (_i, [_vp, _vp, _u64]),
+    "kid_peer_enable": (_i, [C.POINTER(_i), _i]),
+    "kid_sample_ucount_partial": (_i, [_vp, C.POINTER(_vp), _i, _i, _i, _vp]),
+    "kid_sample_ucount_device": (_i, [_vp, C.POINTER(_vp)]),
+    "kid_sample_read_counts": (_i, [_vp, _vp, _vp, _vp]),
+    "kid_device_sync": (_i, [_i]),
     "kid_ucount_range_device": (_i, [_vp, _vp, _u64, _u64, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGS.items():

@@ -228,17 +228,21 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         // table + build scratch (owner array, sort buffers): ~44 B per sector + 36 B per key
         const double slots = layout == KID_LAYOUT_KEYHASH ? 4.0 : (double)KID2_SLOTS_PER_SECTOR;
         auto footprint = [&](int b) { return (double)((uint64_t)1 << b) * (32.0 + 4.0 * slots) + 36.0 * (double)n_keys; };
+        // layout M: half the load again.  A warp of 32 lookups then rarely has a lane that needs the
+        // second, dependent sector load (measured +3 % lookups/s at bact10 scale: 8.6 -> 17 GB of 180).
+        // KID_DB_DENSE=1 keeps the denser table.  The size is a function of n_keys alone, so that
+        // replicas on several GPUs agree slot for slot (the cross-GPU ucount reduction relies on it) ...
+        if (layout == KID_LAYOUT_MINIMIZER && B > lo && B < hi && getenv("KID_DB_DENSE") == nullptr) B++;
+        // ... unless the device cannot hold it: then it shrinks, and says so
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            // layout M with memory to spare: half the load again.  A warp of 32 lookups then rarely
-            // has a lane that needs the second, dependent sector load (measured +3 % lookups/s at
-            // bact10 scale, 8.6 -> 17 GB of 180)
-            if (layout == KID_LAYOUT_MINIMIZER && B > lo && B < hi && footprint(B + 1) < 0.25 * (double)free_b) B++;
-            // keep table + scratch inside the free device memory; a denser table only costs more
-            // second probes
+            const int want = B;
             while (B > lo && footprint(B) > 0.85 * (double)free_b &&
                    (double)((uint64_t)1 << (B - 1)) * slots * 0.8 > (double)n_keys)
                 B--;
+            if (B != want && n_keys < 400000000ull) // (beyond that the nominal size exceeds any one GPU)
+                fprintf(stderr, "kmer_id_b200: device %d has %.1f GB free: probe table 2^%d sectors instead of 2^%d\n",
+                        device, (double)free_b / 1e9, B, want);
         }
     }
 
@@ -703,7 +707,7 @@ static int submit_text(kid_sample *s, HostSlot &h, const uint8_t *seq, const uin
     KID_CUDA(cudaMemcpyAsync(h.seq, seq + b0, bytes, cudaMemcpyHostToDevice, h.stream));
     if (qual) KID_CUDA(cudaMemcpyAsync(h.qual, qual + b0, bytes, cudaMemcpyHostToDevice, h.stream));
     KID_CUDA(cudaMemcpyAsync(h.off, off + r0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h.stream));
-    s->h2d += bytes * (qual ? 2 : 1) + sizeof(uint64_t) * (n + 1);
+    __atomic_fetch_add(&s->h2d, bytes * (qual ? 2 : 1) + sizeof(uint64_t) * (n + 1), __ATOMIC_RELAXED); // (two threads may feed one sample)
     if (use_fused_text_kernel(s->db)) {
         KidClassifyParams p = make_params(s, h.seq, qual ? h.qual : nullptr, h.off, b0, n,
                                           out_taxon ? h.out_taxon : nullptr, out_span ? h.out_span : nullptr);
@@ -715,11 +719,11 @@ static int submit_text(kid_sample *s, HostSlot &h, const uint8_t *seq, const uin
     }
     if (out_taxon) {
         KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
-        s->d2h += sizeof(int32_t) * n;
+        __atomic_fetch_add(&s->d2h, sizeof(int32_t) * n, __ATOMIC_RELAXED);
     }
     if (out_span) {
         KID_CUDA(cudaMemcpyAsync(out_span + 2 * r0, h.out_span, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, h.stream));
-        s->d2h += sizeof(uint32_t) * 2 * n;
+        __atomic_fetch_add(&s->d2h, sizeof(uint32_t) * 2 * n, __ATOMIC_RELAXED);
     }
     return KID_OK;
 }
@@ -736,12 +740,12 @@ static int submit_packed(kid_sample *s, HostSlot &h, const uint32_t *words, uint
     if (rc) return rc;
     if (nw) KID_CUDA(cudaMemcpyAsync(h.words, words + (wa - word0), sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, h.stream));
     KID_CUDA(cudaMemcpyAsync(h.meta, meta + 2 * r0, sizeof(uint2) * (n + 1), cudaMemcpyHostToDevice, h.stream));
-    s->h2d += sizeof(uint32_t) * nw + sizeof(uint2) * (n + 1);
+    __atomic_fetch_add(&s->h2d, sizeof(uint32_t) * nw + sizeof(uint2) * (n + 1), __ATOMIC_RELAXED);
     KidPackedParams p = make_packed_params(s, h.words, h.meta, wa, n, out_taxon ? h.out_taxon : nullptr);
     KID_CUDA(kid_launch_classify3(p, s->db->sm_count, h.stream));
     if (out_taxon) {
         KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
-        s->d2h += sizeof(int32_t) * n;
+        __atomic_fetch_add(&s->d2h, sizeof(int32_t) * n, __ATOMIC_RELAXED);
     }
     return KID_OK;
 }
@@ -905,6 +909,81 @@ int kid_sample_seen_device(kid_sample *s, uint32_t **seen, uint64_t *n_words)
     if (!s || !seen) return fail(KID_EINVAL, "kid_sample_seen_device: NULL argument");
     *seen = s->seen;
     if (n_words) *n_words = s->n_words;
+    return KID_OK;
+}
+
+int kid_peer_enable(const int *devices, int n)
+{
+    if (!devices || n < 1) return fail(KID_EINVAL, "kid_peer_enable: bad argument");
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            if (i == j || devices[i] == devices[j]) continue;
+            int can = 0;
+            KID_CUDA(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+            if (!can) return fail(KID_ECUDA, "device %d cannot map the memory of device %d", devices[i], devices[j]);
+            DeviceGuard guard(devices[i]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); continue; }
+            if (e != cudaSuccess) return fail(KID_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[i], devices[j], cudaGetErrorString(e));
+        }
+    return KID_OK;
+}
+
+int kid_sample_ucount_partial(kid_sample *s, kid_sample *const *shards, int n_shards, int part, int n_parts, void *stream_)
+{
+    if (!s || !shards || n_shards < 1 || n_shards > KID_MAX_OR_SOURCES || n_parts < 1 || part < 0 || part >= n_parts)
+        return fail(KID_EINVAL, "kid_sample_ucount_partial: bad argument");
+    KidPtrList l;
+    for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = nullptr;
+    for (int i = 0; i < n_shards; i++) {
+        const kid_sample *t = shards[i];
+        if (!t) return fail(KID_EINVAL, "kid_sample_ucount_partial: shard %d is NULL", i);
+        const kid_db *a = s->db, *b = t->db;
+        // slot i must mean the same key on every replica
+        if (a->layout != b->layout || a->log2_sectors != b->log2_sectors || a->sub_bits != b->sub_bits ||
+            a->n_distinct != b->n_distinct || a->n_displaced != b->n_displaced || a->n_taxa != b->n_taxa ||
+            s->n_words != t->n_words)
+            return fail(KID_EINVAL, "kid_sample_ucount_partial: shard %d sits on a table replica of another shape "
+                                    "(2^%d vs 2^%d sectors, %llu vs %llu keys)", i, b->log2_sectors, a->log2_sectors,
+                        (unsigned long long)b->n_distinct, (unsigned long long)a->n_distinct);
+        l.p[i] = t->seen;
+    }
+    // equal word ranges, multiples of 4 words; the last part takes the remainder
+    const uint64_t per = (s->n_words / (uint64_t)n_parts) & ~(uint64_t)3;
+    const uint64_t w0 = per * (uint64_t)part;
+    const uint64_t nw = part == n_parts - 1 ? s->n_words - w0 : per;
+    DeviceGuard guard(s->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    KID_CUDA(cudaMemsetAsync(s->ucount, 0, sizeof(int) * (size_t)s->db->n_taxa, stream));
+    if (nw)
+        KID_CUDA(kid_launch_ucount_or(s->db->table_ptr(), s->db->layout, l, n_shards, w0, nw, s->ucount, s->db->n_taxa, stream));
+    return KID_OK;
+}
+
+int kid_sample_ucount_device(kid_sample *s, int32_t **ucount)
+{
+    if (!s || !ucount) return fail(KID_EINVAL, "kid_sample_ucount_device: NULL argument");
+    *ucount = s->ucount;
+    return KID_OK;
+}
+
+int kid_sample_read_counts(kid_sample *s, int32_t *gcount, int32_t *ucount, void *stream_)
+{
+    if (!s) return fail(KID_EINVAL, "kid_sample_read_counts: s is NULL");
+    DeviceGuard guard(s->db->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t nb = sizeof(int) * (size_t)s->db->n_taxa;
+    if (gcount) KID_CUDA(cudaMemcpyAsync(gcount, s->gcount, nb, cudaMemcpyDeviceToHost, stream));
+    if (ucount) KID_CUDA(cudaMemcpyAsync(ucount, s->ucount, nb, cudaMemcpyDeviceToHost, stream));
+    KID_CUDA(cudaStreamSynchronize(stream));
+    return KID_OK;
+}
+
+int kid_device_sync(int device)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(KID_ECUDA, "cudaSetDevice(%d) failed", device);
+    KID_CUDA(cudaDeviceSynchronize());
     return KID_OK;
 }
 

@@ -1,8 +1,12 @@
-// batch_pipeline.hpp - one host thread keeps kSlots packed batches in flight on a kid_sample
-// (kid_classify_packed_async / kid_wait) and hands every finished batch to `done` in stream order.
-// While the GPU works on a batch the reader thread parses and packs the next ones and this thread
+// batch_pipeline.hpp - one host thread keeps packed batches in flight on one or several kid_sample
+// objects (kid_classify_packed_async / kid_wait) and hands every finished batch to `done` in stream
+// order.  While the GPUs work the reader's threads parse and pack the next batches and this thread
 // post-processes the previous one.  Replaces the synchronous per-record call of the reference
 // (process_fqgz -> process_qual, newkmer_10nx.cpp:798-801).
+//
+// Several samples = the shards of ONE logical sample on different GPUs (reads are independent: batches
+// are simply dealt round-robin; multi_gpu.hpp merges the shards at sample end).  Two threads may feed
+// the same kid_sample at once (R1 and R2) as long as they use different slots: slot_base.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -13,41 +17,52 @@
 
 namespace kidhost {
 
-constexpr int kPipelineSlots = 2;                       // submissions in flight per kid_sample
-inline int pipeline_batches() { return pipeline_depth(kPipelineSlots); } // reader batches: in flight + ready + being filled
+constexpr int kPipelineSlots = 2; // submissions in flight per (thread, kid_sample)
+// reader batches so that every slot can be busy while the parse workers stay busy
+inline int pipeline_batches(int n_samples = 1) { return pipeline_depth(kPipelineSlots * n_samples); }
 
 template <class Done>
-void classify_stream(kid_sample *smp, ReadBatchReader &reader, Done &&done)
+void classify_stream(kid_sample *const *smps, int n_smps, int slot_base, ReadBatchReader &reader, Done &&done)
 {
-    std::deque<ReadBatch *> inflight;
+    struct Flight { ReadBatch *b; kid_sample *smp; };
+    std::deque<Flight> inflight;
     size_t submitted = 0;
     auto retire = [&] {
-        ReadBatch *b = inflight.front();
+        const Flight f = inflight.front();
         inflight.pop_front();
-        if (b->slot >= 0 && kid_wait(smp, b->slot) != 0) {
+        if (kid_wait(f.smp, f.b->slot) != 0) {
             fprintf(stderr, "kmer_id_b200: %s\n", kid_last_error());
             exit(1);
         }
-        done(*b);
-        reader.recycle(b);
+        done(*f.b);
+        reader.recycle(f.b);
     };
     for (;;) {
         ReadBatch *b = reader.next();
         const bool last = b->last;
         if (b->n) {
-            if ((int)inflight.size() >= kPipelineSlots) retire(); // frees the slot this batch is about to use
-            b->slot = (int)(submitted++ % kPipelineSlots);
+            // the slot this batch is about to use was last used n_smps * kPipelineSlots submissions ago
+            if ((int)inflight.size() >= n_smps * kPipelineSlots) retire();
+            kid_sample *smp = smps[submitted % (size_t)n_smps];
+            b->slot = slot_base + (int)((submitted / (size_t)n_smps) % kPipelineSlots);
+            submitted++;
             if (kid_classify_packed_async(smp, b->slot, b->words, 0, b->meta, b->n, b->taxon) != 0) {
                 fprintf(stderr, "kmer_id_b200: %s\n", kid_last_error());
                 exit(1);
             }
-            inflight.push_back(b);
+            inflight.push_back(Flight{ b, smp });
         } else {
             reader.recycle(b);
         }
         if (last) break;
     }
     while (!inflight.empty()) retire();
+}
+
+template <class Done>
+void classify_stream(kid_sample *smp, ReadBatchReader &reader, Done &&done)
+{
+    classify_stream(&smp, 1, 0, reader, done);
 }
 
 } // namespace kidhost

@@ -6,13 +6,16 @@
 // <dir><s>_reads.txt; same stdout progress lines.  The per-read work happens in
 // libkmerid_b200.so (include/kmer_id.h); there is no CPU classification path in this program.
 //
-// Extras that do not change the contract: KID_DEVICE=<n> picks the GPU, KID_STATS=1 prints phase
+// Extras that do not change the contract: all visible GPUs are used (KID_GPUS=<k> limits them,
+// KID_DEVICE=<n> pins one; KID_MULTI_MODE=samples deals whole samples to the GPUs instead of splitting
+// every sample over all of them), KID_STATS=1 prints phase
 // timings to stderr, and the parsed probe list is cached next to probes10.txt.gz as
 // probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
 #include "../../include/kmer_id.h"
 #include "batch_pipeline.hpp"
 #include "db_loader.hpp"
 #include "device_warmup.hpp"
+#include "multi_gpu.hpp"
 #include "pgz.hpp"
 #include "read_reader.hpp"
 
@@ -22,7 +25,10 @@
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
+#include <condition_variable>
 #include <iostream>
+#include <mutex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -61,17 +67,18 @@ struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is 
     std::string text; // ">taxon:acc\nbases\n"
 };
 
-// Classify one FASTQ file batch by batch.  direct = R1: append to _reads.txt exactly as process_read
-// :608-614 does.  Otherwise (R2, running concurrently with R1) keep the first SAVENUM records per
-// taxon in stream order; main() writes those that the reference would have written once R1's
-// per-taxon counts are known.
-void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::ofstream *outread,
-              std::vector<SavedRead> *saved)
+// Classify one FASTQ file batch by batch on the given shards (one kid_sample per GPU), using their
+// slots slot_base, slot_base+1.  direct = R1: append to _reads.txt exactly as process_read :608-614
+// does.  Otherwise (R2, running concurrently with R1) keep the first SAVENUM records per taxon in
+// stream order; the caller writes those that the reference would have written once R1's per-taxon
+// counts are known.
+void run_file(kid_sample *const *smps, int n_smps, int slot_base, const std::string &path, SampleState &st,
+              std::ostream *outread, std::vector<SavedRead> *saved, unsigned concurrent_files)
 {
-    // R1 and R2 are inflated at the same time unless KID_SERIAL is set: share the cores
-    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, pipeline_batches(),
-                           default_gz_threads(getenv("KID_SERIAL") ? 1 : 2));
-    classify_stream(smp, reader, [&](const ReadBatch &b) {
+    // R1 and R2 (and, with KID_MULTI_MODE=samples, several samples) are inflated at the same time: share the cores
+    ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, pipeline_batches(n_smps),
+                           default_gz_threads(concurrent_files));
+    classify_stream(smps, n_smps, slot_base, reader, [&](const ReadBatch &b) {
         for (size_t r = 0; r < b.n; r++) {
             const int fin = b.taxon[r];
             if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
@@ -99,12 +106,62 @@ void run_file(kid_sample *smp, const std::string &path, SampleState &st, std::of
         }
     });
 }
+
+// One sample (main():1015-1045) on the shards smps[0..n): R1 then R2 (KID_SERIAL) or both at once.
+// `log` receives what the reference prints for this sample.  counts() merges the shards.
+template <class Counts>
+void process_sample(kid_sample *const *smps, int n_smps, const std::string &dname, const std::string &s, bool serial,
+                    unsigned concurrent_samples, std::ostream &log, Counts &&counts, bool stats, GpuSet *stats_set)
+{
+    const double ts = now();
+    SampleState st, st2;
+    st.gcount_host.assign((size_t)MAXTAR, 0);
+    st2.gcount_host.assign((size_t)MAXTAR, 0);
+    const std::string oname2 = dname + s + "_result.txt", trname = dname + s + "_reads.txt";
+    log << s << std::endl; // :1022
+    std::ofstream outread(trname.c_str(), std::ofstream::out | std::ofstream::trunc);
+    long long tct_total = 0;
+    if (serial) {
+        run_file(smps, n_smps, 0, dname + s + e1, st, &outread, nullptr, concurrent_samples);
+        log << st.tct << " reads loaded" << std::endl; // :1030
+        run_file(smps, n_smps, 0, dname + s + e2, st, &outread, nullptr, concurrent_samples);
+        tct_total = st.tct;
+    } else {
+        // R1 and R2 are inflated, parsed and classified concurrently into the SAME accumulators (gcount and
+        // the seen flags are order independent), each thread on its own pair of slots
+        std::vector<SavedRead> saved;
+        std::thread t2([&] { run_file(smps, n_smps, kPipelineSlots, dname + s + e2, st2, nullptr, &saved, 2 * concurrent_samples); });
+        run_file(smps, n_smps, 0, dname + s + e1, st, &outread, nullptr, 2 * concurrent_samples);
+        log << st.tct << " reads loaded" << std::endl; // :1030
+        t2.join();
+        // an R2 read is written iff fewer than SAVENUM reads of its taxon came before it, R1 first
+        std::vector<int> seen_r2((size_t)MAXTAR, 0);
+        for (const SavedRead &sr : saved) {
+            if (st.gcount_host[(size_t)sr.taxon] + seen_r2[(size_t)sr.taxon] < SAVENUM) outread << sr.text << std::flush;
+            seen_r2[(size_t)sr.taxon]++;
+        }
+        tct_total = st.tct + st2.tct;
+    }
+    std::vector<int32_t> gcount((size_t)MAXTAR), ucount((size_t)MAXTAR);
+    counts(gcount.data(), ucount.data());
+    log << tct_total << " reads loaded" << std::endl; // :1036
+    outread.close();
+    std::ofstream out2(oname2);
+    for (int i = 0; i < MAXTAR; i++) out2 << i << "," << gcount[(size_t)i] << "," << ucount[(size_t)i] << "\n";
+    out2.close();
+    if (stats) {
+        uint64_t lk = 0, hits = 0;
+        if (stats_set) stats_set->counters(lk, hits);
+        else kid_sample_counters(smps[0], &lk, &hits, nullptr, nullptr);
+        fprintf(stderr, "[nk10] %s: %lld reads, %llu lookups, %llu hits in %.3f s\n", s.c_str(), tct_total,
+                (unsigned long long)lk, (unsigned long long)hits, now() - ts);
+    }
+}
 } // namespace
 
 int main(int argc, char *argv[])
 {
     const bool stats = getenv("KID_STATS") != nullptr;
-    const int device = getenv("KID_DEVICE") ? atoi(getenv("KID_DEVICE")) : 0;
     std::string dname = argc > 1 ? argv[1] : "/mnt/dmb/Mark_backup/J/"; // :933-942
     const double t0 = now();
 
@@ -118,22 +175,22 @@ int main(int argc, char *argv[])
     if (!load_tree(tname, MAXTAR, parent, msg)) die(1, msg);
     std::cout << "tree loaded" << std::endl; // :984
 
+    GpuSet gpus;
+    gpus.devices = GpuSet::pick_devices();
     ProbeSet probes;
     // CUDA context creation overlaps the parse.  (Page-locking the batch buffers here as well was
     // measured and dropped: cudaHostAlloc and the parser's page faults fight over the address-space
     // lock, and the load got 1-3 s slower to save 0.3 s on the first sample.)
-    start_device_warmup(device);
+    start_device_warmup(gpus.devices[0]);
     const bool cached = load_probes_cached(pname, probes);
     finish_device_warmup();
     const double t1 = now();
-    kid_db *db = nullptr;
-    if (kid_db_build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), 0, parent.data(), MAXTAR,
-                     device, 0, 0, nullptr, &db) != 0) {
-        if (std::string(kid_last_error()).find("cannot place") != std::string::npos) {
+    if (!gpus.build(probes.keys.data(), probes.taxa.data(), probes.keys.size(), parent.data(), MAXTAR, 0, msg)) {
+        if (msg.find("cannot place") != std::string::npos) {
             std::cout << "out of memory in table " << std::endl; // :258-259
             exit(1);
         }
-        die(1, kid_last_error());
+        die(1, msg);
     }
     std::cout << probes.lines_parsed << " kmers loaded" << std::endl; // :989
     { ProbeSet().keys.swap(probes.keys); std::vector<uint32_t>().swap(probes.taxa); }
@@ -155,72 +212,55 @@ int main(int argc, char *argv[])
         return EXIT_FAILURE;
     }
 
-    // R1 and R2 are inflated, parsed and classified concurrently, each into its own kid_sample
-    // (gcount and the seen flags are order independent); the library merges the two at sample end.
-    // KID_SERIAL=1 processes R1 then R2 on one sample, like the reference.
+    // KID_SERIAL=1 processes R1 then R2 on one thread, like the reference.
     const bool serial = getenv("KID_SERIAL") != nullptr;
-    kid_sample *smp = nullptr, *smp2 = nullptr;
-    if (kid_sample_create(db, &smp) != 0) die(1, kid_last_error());
-    if (!serial && kid_sample_create(db, &smp2) != 0) die(1, kid_last_error());
-    std::vector<int32_t> gcount((size_t)MAXTAR), ucount((size_t)MAXTAR);
-    for (const std::string &s : fnames) {
-        const double ts = now();
-        if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error()); // :1017-1019
-        if (smp2 && kid_sample_begin(smp2, nullptr) != 0) die(1, kid_last_error());
-        SampleState st, st2;
-        st.gcount_host.assign((size_t)MAXTAR, 0);
-        st2.gcount_host.assign((size_t)MAXTAR, 0);
-        const std::string oname2 = dname + s + "_result.txt", trname = dname + s + "_reads.txt";
-        std::cout << s << std::endl; // :1022
-        std::ofstream outread(trname.c_str(), std::ofstream::out | std::ofstream::trunc);
-        long long tct_total = 0;
-        if (serial) {
-            run_file(smp, dname + s + e1, st, &outread, nullptr);
-            std::cout << st.tct << " reads loaded" << std::endl; // :1030
-            run_file(smp, dname + s + e2, st, &outread, nullptr);
-            tct_total = st.tct;
-            if (kid_sample_counts(smp, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
-        } else {
-            std::vector<SavedRead> saved;
-            std::thread t2([&] { run_file(smp2, dname + s + e2, st2, nullptr, &saved); });
-            run_file(smp, dname + s + e1, st, &outread, nullptr);
-            std::cout << st.tct << " reads loaded" << std::endl; // :1030
-            t2.join();
-            // an R2 read is written iff fewer than SAVENUM reads of its taxon came before it, R1 first
-            std::vector<int> seen_r2((size_t)MAXTAR, 0);
-            for (const SavedRead &sr : saved) {
-                if (st.gcount_host[(size_t)sr.taxon] + seen_r2[(size_t)sr.taxon] < SAVENUM) outread << sr.text << std::flush;
-                seen_r2[(size_t)sr.taxon]++;
-            }
-            tct_total = st.tct + st2.tct;
-            kid_sample *both[2] = { smp, smp2 };
-            if (kid_samples_counts(both, 2, gcount.data(), ucount.data(), nullptr) != 0) die(1, kid_last_error());
+    const int n_gpus = (int)gpus.devices.size();
+    const char *mm = getenv("KID_MULTI_MODE");
+    const bool by_sample = n_gpus > 1 && mm && std::string(mm) == "samples";
+    if (!by_sample) {
+        // every sample on all GPUs: its batches are dealt to the GPUs, one exchange at sample end
+        for (const std::string &s : fnames) {
+            if (!gpus.begin(msg)) die(1, msg); // :1017-1019
+            process_sample(gpus.samples.data(), n_gpus, dname, s, serial, 1, std::cout,
+                           [&](int32_t *g, int32_t *u) { if (!gpus.counts(g, u, MAXTAR, msg)) die(1, msg); }, stats, &gpus);
         }
-        std::cout << tct_total << " reads loaded" << std::endl; // :1036
-        outread.close();
-        std::ofstream out2(oname2);
-        for (int i = 0; i < MAXTAR; i++) out2 << i << "," << gcount[(size_t)i] << "," << ucount[(size_t)i] << "\n";
-        out2.close();
-        st.tct = tct_total;
-        if (stats) {
-            uint64_t lk = 0, hits = 0, rd = 0;
-            kid_sample_counters(smp, &lk, &hits, &rd, nullptr);
-            if (smp2) {
-                uint64_t lk2 = 0, hits2 = 0;
-                kid_sample_counters(smp2, &lk2, &hits2, &rd, nullptr);
-                lk += lk2;
-                hits += hits2;
-            }
-            fprintf(stderr, "[nk10] %s: %lld reads, %llu lookups, %llu hits in %.3f s\n", s.c_str(), st.tct,
-                    (unsigned long long)lk, (unsigned long long)hits, now() - ts);
-        }
+    } else {
+        // whole samples dealt to the GPUs: no exchange at all; what each sample prints is held back
+        // until every earlier sample has printed, so stdout reads as if they had run one after another
+        std::vector<std::string> logs(fnames.size());
+        std::vector<char> finished(fnames.size(), 0);
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t next_sample = 0, next_print = 0;
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpus; g++)
+            th.emplace_back([&, g] {
+                kid_sample *smp = gpus.samples[(size_t)g];
+                for (;;) {
+                    size_t i;
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (next_sample >= fnames.size()) return;
+                        i = next_sample++;
+                    }
+                    if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error());
+                    std::ostringstream log;
+                    process_sample(&smp, 1, dname, fnames[i], serial, (unsigned)n_gpus, log,
+                                   [&](int32_t *gc, int32_t *uc) { if (kid_sample_counts(smp, gc, uc, nullptr) != 0) die(1, kid_last_error()); },
+                                   stats, nullptr);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        logs[i] = log.str();
+                        finished[i] = 1;
+                        while (next_print < fnames.size() && finished[next_print]) std::cout << logs[next_print++] << std::flush;
+                    }
+                }
+            });
+        for (auto &t : th) t.join();
     }
     if (stats)
-        fprintf(stderr, "[nk10] %s db %.3f s, build table %.3f s, total %.3f s\n", cached ? "cached" : "parse", t1 - t0,
-                t2 - t1, now() - t0);
+        fprintf(stderr, "[nk10] %s db %.3f s, build table %.3f s, total %.3f s, %d GPU(s)%s\n", cached ? "cached" : "parse",
+                t1 - t0, t2 - t1, now() - t0, n_gpus, n_gpus > 1 ? (by_sample ? ", samples dealt to GPUs" : (gpus.uses_nccl() ? ", reads dealt to GPUs, NCCL all-reduce at sample end" : ", reads dealt to GPUs, host sums at sample end")) : "");
     (void)cached;
-    kid_sample_free(smp);
-    kid_sample_free(smp2);
-    kid_db_free(db);
     return 0;
 }
