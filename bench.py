@@ -332,7 +332,7 @@ def run_ours(args):
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * args.pairs / (ms_per_step / 1e3)
-    reads_kept = counters["reads"]
+    reads_kept = int((dout >= 0).sum().item())  # this rank's reads that passed the length rule (:755)
     if world > 1:  # every read any rank kept is in the reduced gcount exactly once
         t = torch.tensor([reads_kept], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
@@ -485,15 +485,15 @@ def run_ours(args):
 
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(args, wl, hk, ht, parent, gpu_taxa)
-    if world == 1 and not args.no_files_e2e and args.config == "bact10":
-        out["files_e2e"] = files_e2e(args)
+    if not args.no_files_e2e and args.config == "bact10":
+        out["files_e2e"] = files_e2e(args, world)  # the C++ host on all `world` GPUs, in its own process
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def files_e2e(args):
+def files_e2e(args, n_gpus=1):
     """SURVEY.md 8(d) "end-to-end (gz on disk -> _result.txt)": the shipped drop-in
     kmer_id_b200/bin/nk10 on files, after the timed region, in its own process.  The probe DB in the
     reference's text format at the benchmark's scale and three samples of gz FASTQ (generator's
@@ -518,7 +518,7 @@ def files_e2e(args):
                            stdout=subprocess.DEVNULL)
         t0 = time.perf_counter()
         r = subprocess.run([nk10, fq + "/"], cwd=work, capture_output=True, text=True,
-                           env=dict(os.environ, KID_STATS="1", KID_NO_CACHE="1"))
+                           env=dict(os.environ, KID_STATS="1", KID_NO_CACHE="1", KID_GPUS=str(n_gpus)))
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             return {"error": "nk10 exited %d: %s" % (r.returncode, r.stderr[-300:])}
@@ -529,6 +529,7 @@ def files_e2e(args):
                 "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, MEDIAN of %d samples in one "
                         "process (inflate on all host cores, parse + trim + pack, classify); probe DB parsed from gz text"
                         % n_samples,
+                "n_gpus": n_gpus, "mode": (re.findall(r"GPU\(s\)(.*)", r.stderr) or [""])[0].strip(", "),
                 "pairs_per_sample": pairs, "sample_s": per_sample,
                 "first_sample_pairs_per_s": pairs / per_sample[0], "best_sample_pairs_per_s": pairs / min(per_sample),
                 "db_parse_s": float(m.group(1)),

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/kmer_id.h"
@@ -64,10 +65,17 @@ public:
             if (kid_peer_enable(devices.data(), (int)n) != 0) { msg = kid_last_error(); return false; }
 #ifdef KID_HAVE_NCCL
             comms_.resize(n);
+            // whatever NCCL has to say while it starts ("NCCL version ..." with NCCL_DEBUG=VERSION goes to
+            // stdout) must not end up among the reference's stdout lines: stdout is stderr for that long
+            fflush(stdout);
+            const int saved = dup(1);
+            if (saved >= 0) dup2(2, 1);
             if (getenv("KID_NO_NCCL") == nullptr && ncclCommInitAll(comms_.data(), (int)n, devices.data()) == ncclSuccess)
                 nccl_ = true;
             else
                 comms_.clear();
+            fflush(stdout);
+            if (saved >= 0) { dup2(saved, 1); close(saved); }
 #endif
         }
         return true;

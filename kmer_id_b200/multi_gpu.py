@@ -97,8 +97,29 @@ def sample_end_peer(engine: PeerEngine, group=None):
     return engine.gcount.cpu().numpy().copy(), partial.cpu().numpy()
 
 
+def check_replicas_agree(sample, group=None):
+    """Slot i must mean the same key on every rank: the bitmaps are OR-ed by slot index.  kid_db_build
+    sizes the table from the key count alone and places keys deterministically, so replicas built from
+    the same probe list agree - unless a device was short of memory and took a smaller table.  Raise
+    instead of exchanging misaligned bitmaps."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    st = sample.db.stats()
+    mine = torch.tensor([st["n_sectors"], st["table_bytes"], st["n_distinct"], st["n_displaced"],
+                         sample.seen_device()[1], sample.db.n_taxa], dtype=torch.int64,
+                        device=torch.device("cuda", sample.db.device))
+    every = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(every, mine, group=group)
+    for r, other in enumerate(every):
+        if not torch.equal(other, mine):
+            raise RuntimeError(f"kmer_id_b200.multi_gpu: rank {r}'s table replica differs from rank "
+                               f"{dist.get_rank(group)}'s ({other.tolist()} vs {mine.tolist()}): "
+                               "build every replica with the same log2_sectors")
+
+
 def make_engine(sample, stream: int = 0, group=None, prefer_peer: bool = True):
     """PeerEngine when the ranks can map each other's memory, else the NCCL all-to-all engine."""
+    check_replicas_agree(sample, group)
     if prefer_peer and dist.is_initialized() and dist.get_world_size(group) > 1:
         try:
             return PeerEngine(sample, stream, group), "peer"
