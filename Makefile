@@ -12,7 +12,7 @@ CUDA_HOME ?= /usr/local/cuda
 
 CSRC := kmer_id_b200/csrc
 LIB  := kmer_id_b200/libkmerid_b200.so
-LIB_OBJS := $(CSRC)/kid_api.o $(CSRC)/kid_classify.o $(CSRC)/kid_classify2.o $(CSRC)/kid_classify3.o $(CSRC)/kid_pack.o $(CSRC)/kid_pack_host.o $(CSRC)/kid_build_sorted.o $(CSRC)/kid_sample.o
+LIB_OBJS := $(CSRC)/kid_api.o $(CSRC)/kid_classify.o $(CSRC)/kid_classify3.o $(CSRC)/kid_pack.o $(CSRC)/kid_pack_host.o $(CSRC)/kid_build_sorted.o $(CSRC)/kid_sample.o
 
 all: lib tools host oracle
 

@@ -485,8 +485,7 @@ int kid_sample_begin(kid_sample *s, void *stream_)
 
 static cudaError_t launch_classify(const kid_db *db, const KidClassifyParams &p, cudaStream_t stream)
 {
-    return db->layout == KID_LAYOUT_KEYHASH ? kid_launch_classify(p, db->sm_count, stream)
-                                            : kid_launch_classify2(p, db->sm_count, stream);
+    return kid_launch_classify(p, db->sm_count, stream); // layout K only
 }
 
 static KidClassifyParams make_params(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
@@ -528,12 +527,8 @@ static KidPackedParams make_packed_params(kid_sample *s, const uint32_t *words, 
     return p;
 }
 
-// the fused text kernels: layout K (bake-off only) and, on request, the round-1 layout M kernel
-static bool use_fused_text_kernel(const kid_db *db)
-{
-    static const bool forced = getenv("KID_FUSED_TEXT_KERNEL") != nullptr;
-    return db->layout == KID_LAYOUT_KEYHASH || forced;
-}
+// layout K (the key-hashed bake-off table) keeps its own fused text kernel; layout M packs, then scans
+static bool use_fused_text_kernel(const kid_db *db) { return db->layout == KID_LAYOUT_KEYHASH; }
 
 static int reserve_packed(HostSlot &h, size_t words, size_t reads)
 {

@@ -103,11 +103,11 @@ pack2_kernel(uint4 *sectors, size_t n_sectors, const uint32_t *__restrict__ owne
             const uint32_t o = owner[KID2_SLOTS_PER_SECTOR * s + j];
             if (o == kEmpty) continue;
             const uint64_t kw = (keys[o] & KID_MASK60) | KID2_OCC;
-            w[2 * j] = (uint32_t)kw;
-            w[2 * j + 1] = (uint32_t)(kw >> 32);
+            w[j] = (uint32_t)(kw >> 32); // first half: high words (kid_table2.cuh)
+            w[4 + j] = (uint32_t)kw;     // second half: low words
             tx |= (uint64_t)taxa[o] << (KID2_TAXON_BITS * j); // taxon of the first file line of this key
         }
-        w[6] = (uint32_t)tx;
+        w[3] = (uint32_t)tx;
         w[7] = (uint32_t)(tx >> 32);
         sectors[2 * s] = make_uint4(w[0], w[1], w[2], w[3]);
         sectors[2 * s + 1] = make_uint4(w[4], w[5], w[6], w[7]);

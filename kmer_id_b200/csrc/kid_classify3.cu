@@ -65,102 +65,85 @@ __device__ __forceinline__ void build_kmask(WarpStrip &strip, const uint32_t *v,
     __syncwarp();
 }
 
-// the three keys of a sector without its taxa words: 6 registers instead of 8 (the taxa are fetched
-// again for the rare hit), which is what lets four chunks be in flight at 64 registers
-__device__ __forceinline__ void load_sector_keys(const uint4 *p, uint4 &a, uint4 &b)
-{
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(p + 1));
-}
-
 struct ScanState { // all warp-uniform
-    uint32_t fin;                 // running final taxon of the read (:588-595)
-    unsigned long long n_lookups; // getHash calls (:529)
-    unsigned long long n_hits;
+    uint32_t fin;       // running final taxon of the read (:588-595)
+    unsigned n_lookups; // getHash calls (:529); one warp's share of a launch stays far below 2^32
+    unsigned n_hits;
 };
 
-// LOOKUP .. FOLD for N chunks of 32 k-mers whose sector indices are known: all N sector loads are in
-// flight before the first is consumed
-template <int N, bool kKeysOnly, bool kL1>
+// LOOKUP .. FOLD for N chunks of 32 k-mers whose sector indices are known.  All N first halves (high
+// words of the three keys, 4 registers) are in flight before the first is consumed; a lane reads the
+// second half of its sector - from L1 - only if a high word matched (kid_table2.cuh).
+template <int N>
 __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t *key,
-                                              uint32_t *sec, const bool *act, ScanState &st)
+                                              const uint32_t *sec, const bool *act, ScanState &st)
 {
     const unsigned full = 0xFFFFFFFFu;
-    uint4 ea[N], eb[N];
+    uint4 h[N];
     // Inactive lanes (k-mer with an N, or outside the read) read sector 0 instead of branching; their
     // result is ignored.
 #pragma unroll
-    for (int u = 0; u < N; u++) {
-        const uint4 *sp = tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u);
-        if (kKeysOnly) load_sector_keys(sp, ea[u], eb[u]);
-        else if (kL1) // the sector was prefetched into L1
-            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(ea[u].x), "=r"(ea[u].y), "=r"(ea[u].z), "=r"(ea[u].w), "=r"(eb[u].x), "=r"(eb[u].y), "=r"(eb[u].z), "=r"(eb[u].w)
-                         : "l"(sp));
-        else kid2_load_sector(sp, ea[u], eb[u]);
-    }
-    bool hit[N];
-    uint32_t again = 0;
+    for (int u = 0; u < N; u++) h[u] = kid2_load_half(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u));
+    uint32_t taxon[N]; // 0 = miss (taxon 0 is never stored)
+    uint32_t again = 0; // bit u: sector full without the key - it may live further on
 #pragma unroll
     for (int u = 0; u < N; u++) {
-        const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-        const bool h = (ea[u].x == klo && ea[u].y == khi) || (ea[u].z == klo && ea[u].w == khi) ||
-                       (eb[u].x == klo && eb[u].y == khi);
-        hit[u] = act[u] && h;
-        // all three entries carry bit 63 and none matched: the key may live further on
-        const bool more = act[u] && !h && (int32_t)(ea[u].y & ea[u].w & eb[u].y) < 0;
-        again |= more ? (1u << u) : 0u;
-    }
-    if (__any_sync(full, again != 0)) { // the few lanes that met a full sector: all loads first
-#pragma unroll
-        for (int u = 0; u < N; u++)
-            kid2_load_sector_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), ea[u], eb[u], (again >> u) & 1u);
-#pragma unroll
-        for (int u = 0; u < N; u++) {
-            if ((again >> u) & 1u) {
-                const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
-                uint32_t tx = 0;
+        const uint32_t khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+        const uint32_t cand = act[u] ? kid2_candidates(h[u], khi) : 0u;
+        taxon[u] = 0;
+        bool more = act[u] && kid2_full(h[u]);
+        if (__any_sync(full, cand != 0)) { // hits are rare: most chunks skip this
+            if (cand) {
                 int j = 0;
-                const int res = kid2_match(ea[u], eb[u], klo, khi, tx, j);
-                if (res > 0) {
-                    hit[u] = true;
-                    sec[u] = sec[u] + 1; // slack sectors follow the last home sector
-                } else if (res < 0) { // rare: third sector and on
-                    uint64_t slot = 0;
-                    if (kid2_lookup_from(tab, sec[u], key[u], 2, slot)) {
-                        hit[u] = true;
-                        sec[u] = (uint32_t)(slot / KID2_SLOTS_PER_SECTOR);
-                        kid2_load_sector(tab.sectors + 2 * (uint64_t)sec[u], ea[u], eb[u]);
+                uint32_t tx = 0;
+                if (kid2_verify(tab.sectors + 2 * (uint64_t)sec[u], h[u], cand, (uint32_t)key[u], tx, j)) {
+                    taxon[u] = tx;
+                    more = false;
+                    if (tx > 1) { // :596-603 - fire and forget, the OR is idempotent
+                        const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
+                        atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
                     }
                 }
             }
         }
+        again |= more ? (1u << u) : 0u;
     }
-    // SEEN + FOLD, strictly in position order; taxa are only extracted when a chunk has hits
+    if (__any_sync(full, again != 0)) { // the few lanes that met a full sector: their next sectors, all loads first
 #pragma unroll
-    for (int u = 0; u < N; u++) {
-        unsigned m = __ballot_sync(full, hit[u]);
-        if (m) {
-            uint32_t taxon = 0;
-            if (hit[u]) {
-                const uint32_t klo = (uint32_t)key[u], khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+        for (int u = 0; u < N; u++) kid2_load_half_if(tab.sectors + 2 * ((uint64_t)sec[u] + 1), h[u], (again >> u) & 1u);
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            if ((again >> u) & 1u) {
+                const uint32_t khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
+                const uint32_t cand = kid2_candidates(h[u], khi);
                 int j = 0;
-                if (kKeysOnly) { // whichever sector the key was found in: fetch its taxa words now
-                    const uint2 tw = __ldg(reinterpret_cast<const uint2 *>(tab.sectors + 2 * (uint64_t)sec[u]) + 3);
-                    eb[u].z = tw.x;
-                    eb[u].w = tw.y;
+                uint32_t tx = 0;
+                uint64_t slot = 0;
+                bool found = false;
+                if (cand && kid2_verify(tab.sectors + 2 * ((uint64_t)sec[u] + 1), h[u], cand, (uint32_t)key[u], tx, j)) {
+                    found = true;
+                    slot = KID2_SLOTS_PER_SECTOR * ((uint64_t)sec[u] + 1) + (uint64_t)j; // slack sectors follow the last home sector
+                } else if (kid2_full(h[u])) { // rare: third sector and on
+                    tx = kid2_lookup_from(tab, sec[u], key[u], 2, slot);
+                    found = tx != 0;
                 }
-                kid2_match(ea[u], eb[u], klo, khi, taxon, j);
-                if (taxon > 1) { // :596-603 - fire and forget, the OR is idempotent
-                    const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
-                    atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                if (found) {
+                    taxon[u] = tx;
+                    if (tx > 1) atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
                 }
             }
+        }
+    }
+    // FOLD, strictly in position order
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        unsigned m = __ballot_sync(full, taxon[u] != 0);
+        if (m) {
             st.n_hits += __popc(m);
             do { // ordered left fold over the hits of this chunk (:588-595)
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
-                const uint32_t tj = __shfl_sync(full, taxon, src);
+                const uint32_t tj = __shfl_sync(full, taxon[u], src);
                 if (st.fin > 0) { if (tj != st.fin) st.fin = kid_msca(p.tree, tj, st.fin); }
                 else st.fin = tj;
             } while (m);
@@ -225,23 +208,14 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
         const uint32_t grp = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
         sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
     }
+    // every sector index is known before the first load goes out, so that the compiler cannot slide
+    // the tail of MINIM between the loads
+    asm volatile("" ::"r"(sec[0]), "r"(sec[1]), "r"(sec[2]), "r"(sec[3]));
     if (kInFlight == 4) {
-        lookup_chunks<4, true, false>(p, tab, key, sec, act, st);
+        lookup_chunks<4>(p, tab, key, sec, act, st);
     } else {
-        // every sector index is known before the first load goes out, so that the compiler cannot
-        // slide the tail of MINIM between the two loads of the first pair
-        asm volatile("" ::"r"(sec[0]), "r"(sec[1]), "r"(sec[2]), "r"(sec[3]));
-        const bool second = c + 64 <= last; // warp-uniform
-        if (kPrefetch && second) {
-#pragma unroll
-            for (int u = 2; u < 4; u++) {
-                const uint4 *sp = tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u);
-                if (kPrefetch == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
-                else asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
-            }
-        }
-        lookup_chunks<2, false, false>(p, tab, key, sec, act, st);
-        if (second) lookup_chunks<2, false, kPrefetch == 2>(p, tab, key + 2, sec + 2, act + 2, st);
+        lookup_chunks<2>(p, tab, key, sec, act, st);
+        if (c + 64 <= last) lookup_chunks<2>(p, tab, key + 2, sec + 2, act + 2, st); // warp-uniform
     }
 }
 
@@ -403,20 +377,14 @@ cudaError_t launch_variant(const KidPackedParams &p, int sm_count, cudaStream_t 
 
 cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStream_t stream)
 {
-    // Measured on B200 (bact10-scale table, 20 M 150-base reads, tools/gpu_b.sh): two chunks in flight,
-    // then the other two: 16.9 ms; the same with the second pair prefetched into L1: 16.9 ms, into L2:
-    // 22.9 ms; all four in flight with key-only loads (6 registers per sector): 25.7 ms.
-#ifdef KID_TUNE_VARIANTS // experiment builds only: KID_TUNE=<n> picks how the 4 chunks of a block are looked up
+#ifdef KID_TUNE_VARIANTS // experiment builds only: KID_TUNE=<n>
     static const int tune = getenv("KID_TUNE") ? atoi(getenv("KID_TUNE")) : 0;
     switch (tune) {
-    case 1: return launch_variant<2, 1>(p, sm_count, stream); // the other 2 prefetched into L2
-    case 2: return launch_variant<4, 0>(p, sm_count, stream); // all 4 in flight (keys only)
-    case 3: return launch_variant<2, 2>(p, sm_count, stream); // the other 2 prefetched into L1
-    case 4: return launch_variant<2, 0, 8>(p, sm_count, stream);  // 8 reads per group
-    case 5: return launch_variant<2, 0, 12>(p, sm_count, stream); // 12 reads per group
-    case 6: return launch_variant<2, 0, 3>(p, sm_count, stream);  // 3 reads per group
+    case 1: return launch_variant<2, 0>(p, sm_count, stream);     // 2 chunks in flight, then the other 2
+    case 4: return launch_variant<4, 0, 6>(p, sm_count, stream);  // 6 reads per group
+    case 5: return launch_variant<4, 0, 12>(p, sm_count, stream); // 12 reads per group
     default: break;
     }
 #endif
-    return launch_variant<2, 0>(p, sm_count, stream);
+    return launch_variant<4, 0>(p, sm_count, stream); // all 4 chunks of a block in flight
 }

@@ -4,10 +4,10 @@
 #include "kid_table2.cuh"
 
 #define KID_KSIZE 30
-// Layout M kernel: one 1024-thread block per SM at 64 registers per thread.  Measured on B200 with
-// the same 32 resident warps per SM: 4 x 256 threads 99.7 G lookups/s, 2 x 512 104.7 G, 1 x 1024
-// 112.3 G (768 threads at 80 registers: 97.2 G) - one shared-memory gcount histogram per SM instead
-// of four leaves more of the 256 KB array to L1.
+// Layout M scan kernel: one 1024-thread block per SM at 64 registers per thread.  Measured on B200
+// (round 1, same 32 resident warps per SM): 4 x 256 threads 99.7 G lookups/s, 2 x 512 104.7 G,
+// 1 x 1024 112.3 G (768 threads at 80 registers: 97.2 G) - one shared-memory gcount histogram per SM
+// instead of four leaves more of the 256 KB array to L1.
 #ifndef KID_CLASSIFY_THREADS
 #define KID_CLASSIFY_THREADS 1024
 #endif
@@ -81,7 +81,6 @@ extern unsigned long long g_kid_kernel_launches;
 #define KID_COUNT_LAUNCH() (__atomic_add_fetch(&g_kid_kernel_launches, 1ULL, __ATOMIC_RELAXED))
 
 cudaError_t kid_launch_classify(const KidClassifyParams &p, int sm_count, cudaStream_t stream);  // layout K
-cudaError_t kid_launch_classify2(const KidClassifyParams &p, int sm_count, cudaStream_t stream); // layout M
 
 // ---- table build (kid_build_sorted.cu) ----------------------------------------------------------
 struct Kid2BuildStatus {

@@ -1,6 +1,6 @@
 // kid_readprep.cuh - device routines that turn raw read bytes into what the k-mer scan consumes:
 // the exact ACGTacgt(+Uu) test with 2-bit packing, and process_qual's trim (newkmer_10nx.cpp:714-760).
-// Shared by the batch packer (kid_pack.cu) and the fused raw-input kernel (kid_classify2.cu).
+// Used by the batch packer (kid_pack.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

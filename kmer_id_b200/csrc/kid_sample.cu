@@ -37,10 +37,10 @@ kid_ucount_kernel(const void *__restrict__ slots_, const KidPtrList src, int n_s
                 uint32_t taxon;
                 if (LAYOUT == KID_LAYOUT_KEYHASH)
                     taxon = (uint32_t)__ldg(static_cast<const uint64_t *>(slots_) + slot) & KID_TAXON_MASK;
-                else { // packed sector: taxa live in words 6..7
+                else { // packed sector: taxa live in words 3 and 7
                     const uint64_t sec = slot / KID2_SLOTS_PER_SECTOR;
-                    const uint4 hi = __ldg(static_cast<const uint4 *>(slots_) + 2 * sec + 1);
-                    taxon = kid2_taxon_of(hi.z, hi.w, (int)(slot - sec * KID2_SLOTS_PER_SECTOR));
+                    const uint32_t *w = static_cast<const uint32_t *>(slots_) + 8 * sec;
+                    taxon = kid2_taxon_of(__ldg(w + 3), __ldg(w + 7), (int)(slot - sec * KID2_SLOTS_PER_SECTOR));
                 }
                 if (taxon < (uint32_t)n_taxa) atomicAdd(ucount + taxon, 1);
             }

@@ -11,8 +11,16 @@
 //   M(key)   = min_i c(i)                                              strand independent
 //   line     = (M * 0x9E3779B1) >> (32 - L)                            2^L lines of 128 bytes
 //   sector   = 4 * line + top 2 bits of kid_key_hash32(key)            4 sectors per line
-//   sector   = 3 entries: words 0..5 = three 64-bit keys (key | 1<<63, 0 = empty), words 6..7 =
-//              three 21-bit taxa; 12 entries per 128-byte line
+//   sector   = 3 entries, split so that the first 16 bytes decide almost every lookup:
+//                words 0..2  high words of the three keys: (key >> 32) | 1<<31, 0 = empty slot
+//                word  3     low 32 bits of the three 21-bit taxa
+//                words 4..6  low words of the three keys
+//                word  7     high 31 bits of the taxa
+//              12 entries per 128-byte line.  A lookup reads the first half (4 registers) and compares
+//              the 29-bit high words; only a lane whose high word matches (a hit, or one miss in 2^28)
+//              reads the second half - from L1, where its sector just arrived - to compare the low
+//              word and pick up the taxon.  Four chunks of lookups fit the registers that two took
+//              when whole sectors were loaded.
 // Adjacent k-mers of a read share their minimizer in runs of ~7.5, so the 32 lanes of a warp (32
 // consecutive k-mers) touch ~5 distinct lines instead of 32: ~6.5x fewer DRAM line fetches and
 // L2 requests per lookup.  Within the line the key picks the sector, so one lane still reads just
@@ -112,43 +120,48 @@ __host__ __device__ __forceinline__ uint64_t kid2_home_sector(uint32_t minimizer
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ void kid2_load_sector(const uint4 *p, uint4 &a, uint4 &b)
+// first half of a sector (high words + taxa low word); the sector stays in L1 for the second half
+__device__ __forceinline__ uint4 kid2_load_half(const uint4 *p)
 {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "l"(p));
+    uint4 a;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    return a;
 }
-
-// same, but only lanes with pred != 0 issue the load (a/b keep their values otherwise): no branch
-__device__ __forceinline__ void kid2_load_sector_if(const uint4 *p, uint4 &a, uint4 &b, uint32_t pred)
+// same, but only lanes with pred != 0 issue the load (a keeps its value otherwise): no branch
+__device__ __forceinline__ void kid2_load_half_if(const uint4 *p, uint4 &a, uint32_t pred)
 {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-                 "@q ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+                 "@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w)
                  : "l"(p), "r"(pred));
 }
 
-// taxon of entry j (0..2) of a loaded sector: three 21-bit fields in words 6 and 7
-__host__ __device__ __forceinline__ uint32_t kid2_taxon_of(uint32_t w6, uint32_t w7, int j)
+// taxon of entry j (0..2): three 21-bit fields in words 3 (low) and 7 (high)
+__host__ __device__ __forceinline__ uint32_t kid2_taxon_of(uint32_t w3, uint32_t w7, int j)
 {
-    const uint64_t t = ((uint64_t)w7 << 32) | w6;
+    const uint64_t t = ((uint64_t)w7 << 32) | w3;
     return (uint32_t)(t >> (KID2_TAXON_BITS * j)) & (uint32_t)KID2_MAX_TAXA;
 }
 
-// 1 = hit (taxon, slot_in_sector), 0 = final miss (an empty slot), -1 = full sector without match
-__device__ __forceinline__ int kid2_match(const uint4 &a, const uint4 &b, uint32_t want_lo,
-                                          uint32_t want_hi, uint32_t &taxon, int &j)
+// which entries of a first half carry this high word (bit j per entry)
+__device__ __forceinline__ uint32_t kid2_candidates(const uint4 &h, uint32_t want_hi)
 {
-    const bool h0 = a.x == want_lo && a.y == want_hi;
-    const bool h1 = a.z == want_lo && a.w == want_hi;
-    const bool h2 = b.x == want_lo && b.y == want_hi;
-    if (h0 || h1 || h2) {
-        j = h0 ? 0 : (h1 ? 1 : 2);
-        taxon = kid2_taxon_of(b.z, b.w, j);
-        return 1;
-    }
-    // occupied entries carry bit 63: all three high words negative <=> sector full
-    return ((int32_t)(a.y & a.w & b.y) < 0) ? -1 : 0;
+    return (h.x == want_hi ? 1u : 0u) | (h.y == want_hi ? 2u : 0u) | (h.z == want_hi ? 4u : 0u);
+}
+// all three slots occupied (occupied high words carry bit 31)
+__device__ __forceinline__ bool kid2_full(const uint4 &h) { return (int32_t)(h.x & h.y & h.z) < 0; }
+
+// Exact match of one sector given its first half and the candidate mask: reads the second half.
+// 1 = hit (taxon, slot j), 0 = no entry holds the key.
+__device__ __forceinline__ int kid2_verify(const uint4 *sector, const uint4 &h, uint32_t cand, uint32_t want_lo,
+                                           uint32_t &taxon, int &j)
+{
+    const uint4 l = kid2_load_half(sector + 1);
+    const uint32_t ok = cand & ((l.x == want_lo ? 1u : 0u) | (l.y == want_lo ? 2u : 0u) | (l.z == want_lo ? 4u : 0u));
+    if (!ok) return 0;
+    j = __ffs(ok) - 1;
+    taxon = kid2_taxon_of(h.w, l.w, j);
+    return 1;
 }
 
 // continue a lookup from sector `s` (used for the rare full sectors and by the diagnostic kernel)
@@ -158,13 +171,17 @@ __device__ __forceinline__ uint32_t kid2_lookup_from(const Kid2TableView &t, uin
     const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32) | 0x80000000u;
     for (int d = probes_done; d <= t.max_probe; d++) {
         const uint64_t sec = s + (uint64_t)d; // clusters run into the slack sectors, never wrap
-        uint4 a, b;
-        kid2_load_sector(t.sectors + 2 * sec, a, b);
-        uint32_t taxon;
-        int j;
-        const int r = kid2_match(a, b, lo, hi, taxon, j);
-        if (r > 0) { slot = KID2_SLOTS_PER_SECTOR * sec + (uint64_t)j; return taxon; }
-        if (r == 0) return 0;
+        const uint4 h = kid2_load_half(t.sectors + 2 * sec);
+        const uint32_t cand = kid2_candidates(h, hi);
+        if (cand) {
+            uint32_t taxon;
+            int j;
+            if (kid2_verify(t.sectors + 2 * sec, h, cand, lo, taxon, j)) {
+                slot = KID2_SLOTS_PER_SECTOR * sec + (uint64_t)j;
+                return taxon;
+            }
+        }
+        if (!kid2_full(h)) return 0; // an empty slot ends the cluster
     }
     return 0;
 }
