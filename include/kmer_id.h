@@ -77,9 +77,10 @@ void kid_host_free(void *p);
  *                     halves that for ~3 % fewer lookups/s); it shrinks, with a message on stderr,
  *                     only when the device cannot hold it.
  *   n_keys            at most 2^32-2 entries (owner indices are 32-bit during the build).
- * Environment (tuning/test knob): KID_DB_SUB_BITS=2|3|4 forces how many sectors (4, 8, 16) one
+ * Environment (tuning/test knobs): KID_DB_SUB_BITS=2|3|4 forces how many sectors (4, 8, 16) one
  * minimizer addresses in layout M; by default 4, and 8 or 16 only for databases beyond 4e8 keys
- * that device memory keeps densely packed (kid_table2.cuh).
+ * that device memory keeps densely packed (kid_table2.cuh).  KID_DB_MM=20 addresses the table by
+ * 20-mer minimizers instead of 16-mers.  KID_DB_DENSE=1: see log2_sectors.
  */
 int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int keys_on_device,
                  const int32_t *parent, int n_taxa, int device, unsigned flags, int log2_sectors,

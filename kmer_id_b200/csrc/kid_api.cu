@@ -74,6 +74,7 @@ struct kid_db {
     int sm_count = 148;
     int max_probe = 0;
     int sub_bits = 2;           // layout M: log2(sectors per minimizer-addressed group)
+    int mm = 16;                // layout M: minimizer length (16, or 20 for very large databases)
     unsigned flags = 0;
     uint64_t n_sectors = 0;     // addressable home sectors of 32 bytes (K: 4 slots each, M: 3 entries each)
     uint64_t total_sectors = 0; // n_sectors + slack (clusters run past the last home sector, no wrap)
@@ -85,7 +86,7 @@ struct kid_db {
     uint64_t n_slots() const { return (layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR) * total_sectors; }
     const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
     KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
-    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - sub_bits), max_probe, sub_bits }; }
+    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - sub_bits), max_probe, sub_bits, mm }; }
     KidTreeView tree_view() const { return KidTreeView{ tree, n_taxa }; }
 };
 
@@ -246,12 +247,21 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         }
     }
 
-    // several 1e8 keys and more than ~1.5 of them per 128-byte line (memory kept the table small):
-    // the m = 16 minimizers saturate, spread each over 2 or 4 lines (kid_table2.cuh).  KID_DB_SUB_BITS overrides.
-    int sub_bits = 2;
+    // Beyond 4e8 keys the m = 16 minimizers saturate (kid_table2.cuh): a minimizer then addresses 2 or 4
+    // lines instead of one (KID_DB_SUB_BITS=2|3|4 overrides).  KID_DB_MM=20 selects 20-mer minimizers
+    // instead (one line per minimizer again).  Measured at 1.09e9 keys in 2^31 sectors: m = 16 with two
+    // lines per minimizer 24.9 M keys displaced, 107 G lookups/s; m = 20: 31.0 M displaced, 101 G - its
+    // 32-bit ordering hash saturates the same way (the minimum of 11 hashes lies in the lowest twelfth of
+    // the range, so 1e9 winners share ~4e8 values); it would take a second word of identity carried
+    // through the sliding minimum to address lines by.  Hence m = 16 stays the default at every size.
+    int sub_bits = 2, mm = 16;
     if (layout == KID_LAYOUT_MINIMIZER) {
+        if (const char *e = getenv("KID_DB_MM")) {
+            const int v = atoi(e);
+            if (v == 16 || v == KID_MM20) mm = v;
+        }
         const double per_line = (double)n_keys * 4.0 / (double)((uint64_t)1 << B);
-        if (n_keys > 400000000ull) { // below that the minimizers are far from saturated
+        if (mm == 16 && n_keys > 400000000ull) {
             if (per_line > 3.0) sub_bits = 4;
             else if (per_line > 1.5) sub_bits = 3;
         }
@@ -309,6 +319,7 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
         bp.n_sectors = n_sectors;
         bp.slack_sectors = layout == KID_LAYOUT_KEYHASH ? KID1_SLACK_SECTORS : KID2_SLACK_SECTORS;
         bp.sub_bits = sub_bits;
+        bp.mm = mm;
         bp.line_shift = 32 - (B - sub_bits);
         bp.rem_bits = 60 - B;
         bp.n_taxa = (uint32_t)n_taxa;
@@ -334,6 +345,7 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
             KID_CUDA_B(cudaStreamSynchronize(stream));
             db->log2_sectors = B;
             db->sub_bits = sub_bits;
+            db->mm = mm;
             db->n_sectors = n_sectors;
             db->total_sectors = total_sectors;
             db->n_distinct = st.n_distinct;
@@ -935,7 +947,7 @@ int kid_sample_ucount_partial(kid_sample *s, kid_sample *const *shards, int n_sh
         if (!t) return fail(KID_EINVAL, "kid_sample_ucount_partial: shard %d is NULL", i);
         const kid_db *a = s->db, *b = t->db;
         // slot i must mean the same key on every replica
-        if (a->layout != b->layout || a->log2_sectors != b->log2_sectors || a->sub_bits != b->sub_bits ||
+        if (a->layout != b->layout || a->log2_sectors != b->log2_sectors || a->sub_bits != b->sub_bits || a->mm != b->mm ||
             a->n_distinct != b->n_distinct || a->n_displaced != b->n_displaced || a->n_taxa != b->n_taxa ||
             s->n_words != t->n_words)
             return fail(KID_EINVAL, "kid_sample_ucount_partial: shard %d sits on a table replica of another shape "

@@ -46,7 +46,7 @@ home_kernel(const uint64_t *__restrict__ skey, size_t n, KidSortedBuildParams p,
         uint64_t h = ~0ULL;
         if (head) {
             h = p.layout == KID_LAYOUT_KEYHASH ? (kid_hash60(k) >> p.rem_bits)
-                                               : kid2_home_sector(kid_minimizer(k), k, p.line_shift, p.sub_bits);
+                                               : kid2_home_sector(kid_minimizer_mm(k, p.mm), k, p.line_shift, p.sub_bits);
             cnt++;
         }
         home[i] = h;

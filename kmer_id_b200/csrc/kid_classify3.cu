@@ -74,7 +74,7 @@ struct ScanState { // all warp-uniform
 // LOOKUP .. FOLD for N chunks of 32 k-mers whose sector indices are known.  All N first halves (high
 // words of the three keys, 4 registers) are in flight before the first is consumed; a lane reads the
 // second half of its sector - from L1 - only if a high word matched (kid_table2.cuh).
-template <int N>
+template <int N, bool kMerged>
 __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t *key,
                                               const uint32_t *sec, const bool *act, ScanState &st)
 {
@@ -83,22 +83,26 @@ __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Ki
     // Inactive lanes (k-mer with an N, or outside the read) read sector 0 instead of branching; their
     // result is ignored.
 #pragma unroll
-    for (int u = 0; u < N; u++) h[u] = kid2_load_half(tab.sectors + 2 * (uint64_t)(act[u] ? sec[u] : 0u));
+    for (int u = 0; u < N; u++) {
+        const uint32_t si = act[u] ? sec[u] : 0u;
+        h[u] = kid2_load_half(tab.sectors + 2 * (uint64_t)si);
+    }
     uint32_t taxon[N]; // 0 = miss (taxon 0 is never stored)
-    uint32_t again = 0; // bit u: sector full without the key - it may live further on
+    uint32_t again = 0, any_cand = 0; // bit u of again: sector full without the key - it may live further on
 #pragma unroll
     for (int u = 0; u < N; u++) {
         const uint32_t khi = (uint32_t)(key[u] >> 32) | 0x80000000u;
         const uint32_t cand = act[u] ? kid2_candidates(h[u], khi) : 0u;
+        any_cand |= cand;
         taxon[u] = 0;
-        bool more = act[u] && kid2_full(h[u]);
-        if (__any_sync(full, cand != 0)) { // hits are rare: most chunks skip this
+        again |= act[u] && kid2_full(h[u]) ? (1u << u) : 0u;
+        if (!kMerged && __any_sync(full, cand != 0)) { // hits are rare: most chunks skip this
             if (cand) {
                 int j = 0;
                 uint32_t tx = 0;
                 if (kid2_verify(tab.sectors + 2 * (uint64_t)sec[u], h[u], cand, (uint32_t)key[u], tx, j)) {
                     taxon[u] = tx;
-                    more = false;
+                    again &= ~(1u << u);
                     if (tx > 1) { // :596-603 - fire and forget, the OR is idempotent
                         const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
                         atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
@@ -106,7 +110,24 @@ __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Ki
                 }
             }
         }
-        again |= more ? (1u << u) : 0u;
+    }
+    if (kMerged && __any_sync(full, any_cand != 0)) { // hits are rare: reads without any skip this
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const uint32_t cand = act[u] ? kid2_candidates(h[u], (uint32_t)(key[u] >> 32) | 0x80000000u) : 0u;
+            if (cand) {
+                int j = 0;
+                uint32_t tx = 0;
+                if (kid2_verify(tab.sectors + 2 * (uint64_t)sec[u], h[u], cand, (uint32_t)key[u], tx, j)) {
+                    taxon[u] = tx;
+                    again &= ~(1u << u);
+                    if (tx > 1) {
+                        const uint64_t slot = KID2_SLOTS_PER_SECTOR * (uint64_t)sec[u] + (uint64_t)j;
+                        atomicOr(p.seen + (slot >> 5), 1u << (slot & 31));
+                    }
+                }
+            }
+        }
     }
     if (__any_sync(full, again != 0)) { // the few lanes that met a full sector: their next sectors, all loads first
 #pragma unroll
@@ -135,6 +156,12 @@ __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Ki
         }
     }
     // FOLD, strictly in position order
+    if (kMerged) {
+        uint32_t any_hit = 0;
+#pragma unroll
+        for (int u = 0; u < N; u++) any_hit |= taxon[u];
+        if (!__any_sync(full, any_hit != 0)) return;
+    }
 #pragma unroll
     for (int u = 0; u < N; u++) {
         unsigned m = __ballot_sync(full, taxon[u] != 0);
@@ -153,7 +180,7 @@ __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Ki
 
 // KEYS .. FOLD over the k-mers that start at positions [c, c+128) of a read whose first base sits at
 // staged index tbase; `last` = its last k-mer start; kmask bits apply only when `flagged`
-template <int kInFlight, int kPrefetch>
+template <int kInFlight, int kMM, int kVar>
 __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2TableView &tab, const WarpStrip &strip,
                                            int tbase, int c, int last, bool flagged, int lane, ScanState &st)
 {
@@ -161,29 +188,44 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
     const int t0 = tbase + c + lane; // staged index of this lane's base in chunk 0; chunk u: + 32u
     const uint32_t *cw = strip.codes + (t0 >> 4);
     const int sh = (t0 & 15) * 2;
-    uint32_t W[10];
+    constexpr int kW = kMM == 16 ? 10 : 11;
+    uint32_t W[kW];
 #pragma unroll
-    for (int i = 0; i < 10; i++) W[i] = cw[i];
-    uint32_t cm[5]; // 16-mer hashes -> sliding minima
+    for (int i = 0; i < kW; i++) W[i] = cw[i];
+    uint32_t cm[5]; // minimizer-candidate hashes -> sliding minima
     uint64_t key[4];
 #pragma unroll
     for (int u = 0; u < 5; u++) {
-        const uint32_t hi = __funnelshift_l(W[2 * u + 1], W[2 * u], sh);
+        const uint32_t hi = __funnelshift_l(W[2 * u + 1], W[2 * u], sh); // bases 0..15 at this position
         const uint32_t rc = kid_rc16(hi);
-        cm[u] = kid_mm_hash_canon(min(hi, rc));
+        uint32_t lo = 0, rl = 0;
+        if (u < 4 || kMM != 16) {
+            lo = __funnelshift_l(W[2 * u + 2], W[2 * u + 1], sh); // bases 16..31
+            rl = kid_rc16(lo);
+        }
+        if (kMM == 16) {
+            cm[u] = kid_mm_hash_canon(min(hi, rc));
+        } else {
+            // canonical 20-mer as (top 32 bits, low 8 bits): forward = bases 0..19, reverse complement =
+            // that of bases 16..19 in front of that of bases 0..15 (kid_table2.cuh)
+            const uint32_t ft = hi, fl = lo >> 24;
+            const uint32_t rt = ((rl & 0xFFu) << 24) | (rc >> 8), rlo = rc & 0xFFu;
+            const bool fwd = ft < rt || (ft == rt && fl < rlo);
+            cm[u] = kid_mm20_hash_canon(fwd ? ft : rt, fwd ? fl : rlo);
+        }
         if (u < 4) {
             // forward key = first 30 of the 32 bases at this position; the reverse complement of 32
             // bases is rc16(low half) : rc16(high half), its low 60 bits that of the first 30 bases
-            const uint32_t lo = __funnelshift_l(W[2 * u + 2], W[2 * u + 1], sh);
             const uint64_t kf = (((uint64_t)hi << 32) | lo) >> 4;
-            const uint64_t kr = (((uint64_t)kid_rc16(lo) << 32) | rc) & KID_MASK60;
+            const uint64_t kr = (((uint64_t)rl << 32) | rc) & KID_MASK60;
             key[u] = kf < kr ? kf : kr; // :528
         }
     }
-    // MINIM: window minimum over 15 consecutive positions (1 + 2 + 4 + 7 doubling)
+    // MINIM: window minimum over the 15 (m = 16) or 11 (m = 20) candidate positions of a 30-mer by
+    // doubling: 1 + 2 + 4 + 7 resp. 1 + 2 + 4 + 3
 #pragma unroll
     for (int step = 0; step < 4; step++) {
-        const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 7;
+        const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : (kMM == 16 ? 7 : 3);
         const int src = lane + d; // shfl takes the source lane modulo 32
         const bool wrap = lane + d >= 32;
         uint32_t s[5];
@@ -193,18 +235,28 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
         for (int u = 0; u < 4; u++) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
         if (step < 3) cm[4] = min(cm[4], wrap ? 0xFFFFFFFFu : s[4]);
     }
-    // which of the 128 positions are k-mer starts: inside the read (first nv positions of the block)
-    // and, for a read with non-ACGT bases, the start of a run of 30 valid bases.  Warp-uniform masks,
-    // position 32u+j in bit 31-j of word u.
+    // which of the 128 positions are k-mer starts: inside the read (the first nvb positions of the
+    // block) and, for a read with non-ACGT bases, the start of a run of 30 valid bases (kmask: position
+    // 32u+j in bit 31-j of word u, warp-uniform)
     bool act[4];
     uint32_t sec[4];
+    const int nvb = last - c + 1; // >= 1
+    if ((kVar & 2) && !flagged) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) act[u] = lane < nvb - 32 * u;
+        st.n_lookups += (unsigned)min(nvb, 128); // each is one getHash call (:529)
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int nv = nvb - 32 * u;
+            uint32_t m = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : 0xFFFFFFFFu << (32 - nv));
+            if (flagged) m &= strip.kmask[(c >> 5) + u];
+            st.n_lookups += __popc(m);
+            act[u] = (int32_t)(m << lane) < 0;
+        }
+    }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-        const int nv = last - c - 32 * u + 1;
-        uint32_t m = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : 0xFFFFFFFFu << (32 - nv));
-        if (flagged) m &= strip.kmask[(c >> 5) + u];
-        st.n_lookups += __popc(m); // each is one getHash call (:529)
-        act[u] = (int32_t)(m << lane) < 0;
         const uint32_t grp = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
         sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
     }
@@ -212,14 +264,14 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
     // the tail of MINIM between the loads
     asm volatile("" ::"r"(sec[0]), "r"(sec[1]), "r"(sec[2]), "r"(sec[3]));
     if (kInFlight == 4) {
-        lookup_chunks<4>(p, tab, key, sec, act, st);
+        lookup_chunks<4, (kVar & 1) != 0>(p, tab, key, sec, act, st);
     } else {
-        lookup_chunks<2>(p, tab, key, sec, act, st);
-        if (c + 64 <= last) lookup_chunks<2>(p, tab, key + 2, sec + 2, act + 2, st); // warp-uniform
+        lookup_chunks<2, (kVar & 1) != 0>(p, tab, key, sec, act, st);
+        if (c + 64 <= last) lookup_chunks<2, (kVar & 1) != 0>(p, tab, key + 2, sec + 2, act + 2, st); // warp-uniform
     }
 }
 
-template <bool SMEM_HIST, int kInFlight, int kPrefetch, int kGroup>
+template <bool SMEM_HIST, int kInFlight, int kMM, int kGroup, int kVar>
 __global__ void __launch_bounds__(KID_CLASSIFY_THREADS, 1)
 kid_classify3_kernel(const KidPackedParams p)
 {
@@ -293,7 +345,7 @@ kid_classify3_kernel(const KidPackedParams p)
                         const int last = tl - KID_KSIZE;
                         if (flagged) build_kmask(strip, p.words + wf + ((tl + 15) >> 4), (tl + 31) >> 5, (last >> 5) + 1, lane);
                         const int tbase = (int)(wf - base) * 16;
-                        for (int c = 0; c <= last; c += 128) scan_block<kInFlight, kPrefetch>(p, tab, strip, tbase, c, last, flagged, lane, st);
+                        for (int c = 0; c <= last; c += 128) scan_block<kInFlight, kMM, kVar>(p, tab, strip, tbase, c, last, flagged, lane, st);
                     }
                     finish_read(r0 + i, kept);
                 }
@@ -318,7 +370,7 @@ kid_classify3_kernel(const KidPackedParams p)
                         __syncwarp();
                         if (flagged)
                             build_kmask(strip, p.words + wf + cwords + (wb >> 5), vwords - (wb >> 5), (wlast >> 5) + 1, lane);
-                        for (int c = 0; c <= wlast; c += 128) scan_block<kInFlight, kPrefetch>(p, tab, strip, 0, c, wlast, flagged, lane, st);
+                        for (int c = 0; c <= wlast; c += 128) scan_block<kInFlight, kMM, kVar>(p, tab, strip, 0, c, wlast, flagged, lane, st);
                     }
                 }
                 finish_read(r0 + s, kept);
@@ -340,11 +392,11 @@ kid_classify3_kernel(const KidPackedParams p)
     }
 }
 
-template <bool H, int F, int PF, int G>
+template <bool H, int F, int MM, int G, int V>
 cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WarpStrip) * kWarpsPerBlock + (H ? (size_t)p.tree.n_taxa * 4 : 0);
-    auto kern = kid_classify3_kernel<H, F, PF, G>;
+    auto kern = kid_classify3_kernel<H, F, MM, G, V>;
     cudaError_t err = cudaSuccess;
     if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -366,11 +418,20 @@ cudaError_t launch_one(const KidPackedParams &p, int sm_count, cudaStream_t stre
     return cudaGetLastError();
 }
 
-template <int F, int PF, int G = kGroupDefault>
-cudaError_t launch_variant(const KidPackedParams &p, int sm_count, cudaStream_t stream)
+template <int F, int MM, int G, int V>
+cudaError_t launch_hist(const KidPackedParams &p, int sm_count, cudaStream_t stream)
 {
     const bool hist = (size_t)p.tree.n_taxa * 4 <= KID_SMEM_HIST_MAX_BYTES;
-    return hist ? launch_one<true, F, PF, G>(p, sm_count, stream) : launch_one<false, F, PF, G>(p, sm_count, stream);
+    return hist ? launch_one<true, F, MM, G, V>(p, sm_count, stream) : launch_one<false, F, MM, G, V>(p, sm_count, stream);
+}
+
+// measured (tools/gpu_i.sh, 20 M reads): per-chunk votes + range masks 15.69 ms; one vote per block 16.27;
+// lane compare instead of range masks 15.53; both 15.94
+constexpr int kVarDefault = 2;
+template <int F, int G = kGroupDefault, int V = kVarDefault>
+cudaError_t launch_variant(const KidPackedParams &p, int sm_count, cudaStream_t stream)
+{
+    return p.table2.mm == KID_MM20 ? launch_hist<F, KID_MM20, G, V>(p, sm_count, stream) : launch_hist<F, 16, G, V>(p, sm_count, stream);
 }
 
 } // namespace
@@ -380,11 +441,11 @@ cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStr
 #ifdef KID_TUNE_VARIANTS // experiment builds only: KID_TUNE=<n>
     static const int tune = getenv("KID_TUNE") ? atoi(getenv("KID_TUNE")) : 0;
     switch (tune) {
-    case 1: return launch_variant<2, 0>(p, sm_count, stream);     // 2 chunks in flight, then the other 2
-    case 4: return launch_variant<4, 0, 6>(p, sm_count, stream);  // 6 reads per group
-    case 5: return launch_variant<4, 0, 12>(p, sm_count, stream); // 12 reads per group
+    case 1: return launch_variant<2>(p, sm_count, stream);     // 2 chunks in flight, then the other 2
+    case 2: return launch_variant<4, kGroupDefault, 0>(p, sm_count, stream); // range masks instead of the lane compare
+    case 3: return launch_variant<4, kGroupDefault, 3>(p, sm_count, stream); // one vote for all candidates / hits of a block
     default: break;
     }
 #endif
-    return launch_variant<4, 0>(p, sm_count, stream); // all 4 chunks of a block in flight
+    return launch_variant<4>(p, sm_count, stream); // all 4 chunks of a block in flight
 }

@@ -98,6 +98,7 @@ struct KidSortedBuildParams {
     uint64_t slack_sectors; // extra sectors after the last home sector (no wrap-around)
     int line_shift;        // layout M: 32 - log2(groups)
     int sub_bits;          // layout M: log2(sectors per minimizer-addressed group), 2..4
+    int mm;                // layout M: minimizer length, 16 or 20
     int rem_bits;          // layout K: 60 - log2_sectors
     uint32_t n_taxa, max_taxon, max_disp;
 };

@@ -78,7 +78,7 @@ __global__ void kid_lookup2_kernel(Kid2TableView t, const uint64_t *keys, size_t
          i += (size_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i] & KID_MASK60;
         uint64_t slot;
-        out[i] = kid2_lookup_from(t, kid2_home_sector(kid_minimizer(key), key, t.line_shift, t.sub_bits), key, 0, slot);
+        out[i] = kid2_lookup_from(t, kid2_home_sector(kid_minimizer_mm(key, t.mm), key, t.line_shift, t.sub_bits), key, 0, slot);
     }
 }
 

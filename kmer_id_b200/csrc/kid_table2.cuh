@@ -50,6 +50,7 @@ struct Kid2TableView {
     int line_shift;       // 32 - log2(groups): the minimizer picks a group of 2^sub_bits sectors
     int max_probe;        // longest displacement (in sectors) any key needed at build time
     int sub_bits;         // 2 = one 128-byte line per minimizer (default); 3, 4 for very large DBs
+    int mm;               // minimizer length in bases: 16 (default) or 20 (databases beyond ~4e8 keys)
 };
 
 // reverse complement of a 16-mer held in 32 bits (first base in the top pair)
@@ -99,6 +100,39 @@ __host__ __device__ __forceinline__ uint32_t kid_minimizer(uint64_t key)
         m = c < m ? c : m;
     }
     return m;
+}
+
+// ---- m = 20 for very large databases ------------------------------------------------------------
+// Only ~10 % of the 2^31 canonical 16-mers ever win a 15-way minimum, so beyond a few 1e8 keys several
+// keys share every minimizer and pile into its 12-entry line.  A 20-mer minimizer (11 windows, 2^39
+// canonical values) gives practically every key of a 1e9-key database its own.  The canonical 20-mer
+// is kept as (top 32 bits, low 8 bits); only the order of the hash matters.
+#define KID_MM20 20
+#define KID_MM20_WINDOWS (30 - KID_MM20 + 1) /* 11 */
+__host__ __device__ __forceinline__ uint32_t kid_mm20_hash_canon(uint32_t top, uint32_t low8)
+{
+    uint32_t x = top * 0x9E3779B1u ^ low8 * 0xC2B2AE3Du;
+    x ^= x >> 15;
+    x *= 0x85EBCA77u;
+    return x;
+}
+// minimizer hash of a 60-bit key with 20-mer candidates (build side)
+__host__ __device__ __forceinline__ uint32_t kid_minimizer20(uint64_t key)
+{
+    uint32_t m = 0xFFFFFFFFu;
+    for (int i = 0; i < KID_MM20_WINDOWS; i++) {
+        const uint64_t f = (key >> (2 * (KID_MM20_WINDOWS - 1 - i))) & ((1ULL << 40) - 1ULL); // bases i..i+19
+        // reverse complement of 20 bases: that of the 16 first bases below that of the last 4
+        const uint64_t r = ((uint64_t)(kid_rc16((uint32_t)(f << 24)) & 0xFFu) << 32) | kid_rc16((uint32_t)(f >> 8));
+        const uint64_t c = f < r ? f : r;
+        const uint32_t h = kid_mm20_hash_canon((uint32_t)(c >> 8), (uint32_t)(c & 0xFFu));
+        m = h < m ? h : m;
+    }
+    return m;
+}
+__host__ __device__ __forceinline__ uint32_t kid_minimizer_mm(uint64_t key, int mm)
+{
+    return mm == KID_MM20 ? kid_minimizer20(key) : kid_minimizer(key);
 }
 
 // the key's own hash picks the sector inside the minimizer's group: its top sub_bits bits

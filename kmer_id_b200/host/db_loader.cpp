@@ -1,4 +1,6 @@
 #include "db_loader.hpp"
+
+#include <new>
 #include "gz_lines.hpp"
 
 #include <algorithm>
@@ -283,9 +285,19 @@ bool load_probes_cached(const std::string &path, ProbeSet &out, bool target_sign
                       h.src_size == (uint64_t)st.st_size &&
                       h.src_mtime_ns == (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec &&
                       h.target_signed == (uint32_t)target_signed;
+            // a truncated or damaged cache must fall back to the text, not die in resize()
+            struct stat cst;
+            ok = ok && fstat(fileno(f), &cst) == 0 && h.n_entries < 0xFFFFFFFFull &&
+                 (uint64_t)cst.st_size == sizeof h + 12ull * h.n_entries;
             if (ok) {
-                out.keys.resize((size_t)h.n_entries);
-                out.taxa.resize((size_t)h.n_entries);
+                try {
+                    out.keys.resize((size_t)h.n_entries);
+                    out.taxa.resize((size_t)h.n_entries);
+                } catch (const std::bad_alloc &) {
+                    ok = false;
+                }
+            }
+            if (ok) {
                 ok = fread(out.keys.data(), 8, out.keys.size(), f) == out.keys.size() &&
                      fread(out.taxa.data(), 4, out.taxa.size(), f) == out.taxa.size();
                 out.lines_parsed = h.lines_parsed;

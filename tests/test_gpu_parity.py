@@ -414,3 +414,21 @@ def test_wide_minimizer_groups(sub_bits, monkeypatch):
         osamp.reset()
         _check_batch(gs, osamp, H.make_reads(rng, db, 3000, ragged=True))
         _check_counts(gs, osamp)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(lower_rate=0.05, n_rate=0.02), dict(length=250, bad_tail=0.6), dict(ragged=True)])
+def test_20mer_minimizers(kw, monkeypatch):
+    """Layout M with 20-mer minimizers (11 windows) instead of 16-mers (KID_DB_MM=20, an option for
+    very large databases): the table is placed differently, the answers are the same - also on a table
+    loaded so high that keys get displaced."""
+    monkeypatch.setenv("KID_DB_MM", "20")
+    rng = np.random.default_rng(400 + len(kw))
+    db = H.make_db(rng, 30000, n_dup=500, n_zero=50)
+    odb, osamp = _oracle(db)
+    for tkw in ({}, {"log2_sectors": 14}):  # default size, and 16384 sectors for ~30000 keys
+        gdb, gs = _gpu(db, LAYOUT_M, **tkw)
+        want = np.array([odb.lookup(int(k)) for k in db.keys[:3000]], dtype=np.uint32)
+        assert np.array_equal(gdb.lookup(db.keys[:3000]), want)
+        osamp.reset()
+        _check_batch(gs, osamp, H.make_reads(rng, db, 3000, **kw))
+        _check_counts(gs, osamp)
