@@ -73,6 +73,9 @@ def parse_args():
                     help="skip the gz-files-on-disk -> _result.txt run of the nk10 drop-in")
     ap.add_argument("--layout", default="M", choices=["M", "K"], help="table layout (M = minimizer, default)")
     ap.add_argument("--log2-sectors", type=int, default=0, help="table size override (0 = library default)")
+    ap.add_argument("--parity-reads", type=int, default=-1,
+                    help="N > 1: reads of rank 0 checked against the CPU oracle over the full probe list "
+                         "(-1 = 100000, but 0 for --config x10 whose oracle needs ~105 GB of host RAM and minutes)")
     ap.add_argument("--chunk-reads", type=int, default=0, help="reads per H2D chunk of the host entry points (0 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=80.0,
                     help="CPU seconds the reference arm may spend classifying (all steps together)")
@@ -84,6 +87,8 @@ def parse_args():
     if a.pairs <= 0:
         a.pairs = a.cfg["pairs"]
     a.read_len = a.cfg["read_len"]
+    if a.parity_reads < 0:
+        a.parity_reads = 0 if a.config == "x10" else 100_000
     return a
 
 
@@ -279,7 +284,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     st = db.stats()
-    keep_keys = world == 1 and not args.no_cpu_baseline or world > 1 and rank == 0
+    keep_keys = world == 1 and not args.no_cpu_baseline or world > 1 and rank == 0 and args.parity_reads > 0
     hk = dk.cpu().numpy().view(np.uint64) if keep_keys else None  # the oracle checks below want the probe list
     ht = dt.cpu().numpy().view(np.uint32) if keep_keys else None
     del dk, dt
@@ -434,8 +439,8 @@ def run_ours(args):
 
     # ---- N > 1: rank 0 checks its first reads against the CPU oracle (N = 1 does it in cpu_baseline)
     parity_n = 0
-    if world > 1 and rank == 0:
-        parity_n = oracle_check(args, wl, hk, ht, parent, gpu_taxa, 100_000)
+    if world > 1 and rank == 0 and args.parity_reads > 0:
+        parity_n = oracle_check(args, wl, hk, ht, parent, gpu_taxa, args.parity_reads)
     if rank != 0:
         if world > 1:
             dist.barrier()
