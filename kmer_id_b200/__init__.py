@@ -20,7 +20,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmerid_b200.so")
+LIB_PATH = os.environ.get("KID_LIB_PATH") or os.path.join(_HERE, "libkmerid_b200.so")  # (KID_LIB_PATH: A/B builds in experiments)
 KSIZE = 30
 
 if not os.path.exists(LIB_PATH):

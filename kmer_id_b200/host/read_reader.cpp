@@ -47,6 +47,9 @@ void pinned_put(void *p, size_t bytes)
 }
 size_t batch_words(size_t max_reads, size_t cap_bytes) { return kid_pack_bound(max_reads, cap_bytes) + 16; }
 
+// text bytes per super-block of the parallel gz FASTQ path
+size_t parallel_block_bytes(size_t max_bytes) { return std::max<size_t>(4096, std::min<size_t>(max_bytes, (size_t)8 << 20)); }
+
 unsigned parse_threads_default()
 {
     if (const char *e = getenv("KID_PARSE_THREADS")) return (unsigned)std::max(0, atoi(e));
@@ -109,10 +112,20 @@ ReadBatchReader::ReadBatchReader(ReadFormat fmt, const std::string &path, size_t
 {
     const bool fastq = fmt == ReadFormat::GzFastq || fmt == ReadFormat::PlainFastq;
     parse_threads_ = fmt == ReadFormat::GzFastq && mode == BatchMode::Packed ? parse_threads_default() : 0;
+    // the parallel gz FASTQ path fills one batch per super-block of text (parallel_block_bytes()): size the
+    // page-locked buffers for that (ordinary 100-300-base records; the dispatcher grows a batch when a
+    // super-block needs more), not for max_bytes of bases - page-locking is slow
+    size_t cap_bytes = max_bytes_ + kRefLineLimit, cap_reads = max_reads_;
+    if (parse_threads_ > 0) {
+        // a super-block is closed by the line block that takes it past the target (<= 4 MiB more)
+        const size_t target = parallel_block_bytes(max_bytes_) + std::min<size_t>(4u << 20, parallel_block_bytes(max_bytes_));
+        cap_bytes = target / 2 + kRefLineLimit + 64;
+        cap_reads = std::max<size_t>(1024, target / 64);
+    }
     for (int i = 0; i < depth; i++) {
         auto b = std::make_unique<ReadBatch>();
         b->has_qual = fastq;
-        alloc_batch(*b, max_bytes_ + kRefLineLimit, max_reads_);
+        alloc_batch(*b, cap_bytes, cap_reads);
         free_.push_back(b.get());
         pool_.push_back(std::move(b));
     }
@@ -391,7 +404,7 @@ void ReadBatchReader::publish_ordered(uint64_t index, ReadBatch *b)
 
 void ReadBatchReader::run_gz_fastq_parallel(const std::string &path)
 {
-    const size_t target = std::max<size_t>(4096, std::min<size_t>(max_bytes_, (size_t)8 << 20)); // text bytes per super-block
+    const size_t target = parallel_block_bytes(max_bytes_);
     GzLineBlocks src(path, std::min<size_t>(4u << 20, target), gz_threads_);
 
     std::mutex qmu;
@@ -497,8 +510,12 @@ void ReadBatchReader::run_gz_fastq_parallel(const std::string &path)
         ReadBatch *b = get_free();
         const size_t need_reads = sb->lines / 4 + 2, need_bytes = sb->bytes / 2 + kRefLineLimit + 64;
         if (need_reads > b->cap_reads || need_bytes > b->cap_bytes) {
+            // rare (an unusually large line block, or very short records): grow in coarse steps so that
+            // the page-locked pool keeps handing out buffers of the same few sizes
+            auto up = [](size_t v, size_t q) { return (v + v / 4 + q - 1) / q * q; };
             free_batch(*b);
-            alloc_batch(*b, std::max(need_bytes, b->cap_bytes), std::max(need_reads + need_reads / 4, b->cap_reads));
+            alloc_batch(*b, need_bytes > b->cap_bytes ? up(need_bytes, (size_t)1 << 20) : b->cap_bytes,
+                        need_reads > b->cap_reads ? up(need_reads, (size_t)1 << 16) : b->cap_reads);
         }
         sb->batch = b;
         {
