@@ -74,7 +74,7 @@ struct ScanState { // all warp-uniform
 // LOOKUP .. FOLD for N chunks of 32 k-mers whose sector indices are known.  All N first halves (high
 // words of the three keys, 4 registers) are in flight before the first is consumed; a lane reads the
 // second half of its sector - from L1 - only if a high word matched (kid_table2.cuh).
-template <int N, bool kMerged>
+template <int N, bool kMerged, bool kNoL1>
 __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Kid2TableView &tab, const uint64_t *key,
                                               const uint32_t *sec, const bool *act, ScanState &st)
 {
@@ -85,7 +85,9 @@ __device__ __forceinline__ void lookup_chunks(const KidPackedParams &p, const Ki
 #pragma unroll
     for (int u = 0; u < N; u++) {
         const uint32_t si = act[u] ? sec[u] : 0u;
-        h[u] = kid2_load_half(tab.sectors + 2 * (uint64_t)si);
+        if (kNoL1) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                : "=r"(h[u].x), "=r"(h[u].y), "=r"(h[u].z), "=r"(h[u].w) : "l"(tab.sectors + 2 * (uint64_t)si));
+        else h[u] = kid2_load_half(tab.sectors + 2 * (uint64_t)si);
     }
     uint32_t taxon[N]; // 0 = miss (taxon 0 is never stored)
     uint32_t again = 0, any_cand = 0; // bit u of again: sector full without the key - it may live further on
@@ -264,10 +266,10 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
     // the tail of MINIM between the loads
     asm volatile("" ::"r"(sec[0]), "r"(sec[1]), "r"(sec[2]), "r"(sec[3]));
     if (kInFlight == 4) {
-        lookup_chunks<4, (kVar & 1) != 0>(p, tab, key, sec, act, st);
+        lookup_chunks<4, (kVar & 1) != 0, (kVar & 4) != 0>(p, tab, key, sec, act, st);
     } else {
-        lookup_chunks<2, (kVar & 1) != 0>(p, tab, key, sec, act, st);
-        if (c + 64 <= last) lookup_chunks<2, (kVar & 1) != 0>(p, tab, key + 2, sec + 2, act + 2, st); // warp-uniform
+        lookup_chunks<2, (kVar & 1) != 0, (kVar & 4) != 0>(p, tab, key, sec, act, st);
+        if (c + 64 <= last) lookup_chunks<2, (kVar & 1) != 0, (kVar & 4) != 0>(p, tab, key + 2, sec + 2, act + 2, st); // warp-uniform
     }
 }
 
@@ -426,7 +428,7 @@ cudaError_t launch_hist(const KidPackedParams &p, int sm_count, cudaStream_t str
 }
 
 // measured (tools/gpu_i.sh, 20 M reads): per-chunk votes + range masks 15.69 ms; one vote per block 16.27;
-// lane compare instead of range masks 15.53; both 15.94
+// lane compare instead of range masks 15.53; both 15.94; first halves bypassing L1 (bit 2): 16.22
 constexpr int kVarDefault = 2;
 template <int F, int G = kGroupDefault, int V = kVarDefault>
 cudaError_t launch_variant(const KidPackedParams &p, int sm_count, cudaStream_t stream)
@@ -444,6 +446,7 @@ cudaError_t kid_launch_classify3(const KidPackedParams &p, int sm_count, cudaStr
     case 1: return launch_variant<2>(p, sm_count, stream);     // 2 chunks in flight, then the other 2
     case 2: return launch_variant<4, kGroupDefault, 0>(p, sm_count, stream); // range masks instead of the lane compare
     case 3: return launch_variant<4, kGroupDefault, 3>(p, sm_count, stream); // one vote for all candidates / hits of a block
+    case 4: return launch_variant<4, kGroupDefault, 6>(p, sm_count, stream); // first halves bypass L1
     default: break;
     }
 #endif

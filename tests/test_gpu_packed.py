@@ -180,3 +180,26 @@ def test_packed_rejected_for_keyhash_layout():
     words, meta = kid.pack_reads(b.seq, b.qual, b.off)
     with pytest.raises(kid.KidError):
         gs.classify_packed_host(words, meta, b.n, None)
+
+
+def test_more_taxa_than_the_shared_histogram_holds():
+    """gcount lives in a shared-memory histogram up to 24 576 taxa (96 KB); beyond that the kernel adds to
+    global memory directly.  40 000 taxa in a random recursive tree: same answers."""
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(34)
+    n = 40_000
+    parent = np.ones(n, np.int32)
+    for v in range(2, n):
+        parent[v] = int(rng.integers(1, v)) if v > 50 else max(1, v - 1)
+    keys = H.canonical(rng.integers(0, 1 << 60, size=20000, dtype=np.uint64))
+    db = H.SynthDB(keys=keys, taxa=rng.integers(2, n, size=keys.size).astype(np.uint32), parent=parent)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batch = H.make_reads(rng, db, 3000, n_rate=0.002)
+    fin_o, _ = osamp.classify(batch.seq, batch.qual, batch.off)
+    words, meta = kid.pack_reads(batch.seq, batch.qual, batch.off)
+    out = np.full(batch.n, -2, np.int32)
+    gs.classify_packed_host(words, meta, batch.n, out)
+    assert np.array_equal(out, fin_o)
+    _check_counts(gs, osamp)
+    assert (fin_o > 24_576).sum() > 100
