@@ -14,9 +14,10 @@ independently classified reads.
 
   value  pairs/s with the TEXT batch (bases + qualities) already resident in HBM: kid_pack_kernel
          (trim + 2-bit pack) + kid_classify3_kernel per step, CUDA events on the launching stream
-  e2e    pairs/s through kid_classify_packed_host from pinned HOST buffers holding the packed batch a
-         parser produces with kid_pack_reads (H2D + kernel + D2H inside the region); e2e_text is the
-         same through kid_classify_host from bases + qualities (what round 1 reported as e2e)
+  e2e    pairs/s through kid_classify_dense_host from pinned HOST buffers holding the dense batch a
+         parser produces with kid_pack_reads_dense (H2D + expand + scan + D2H inside the region);
+         e2e_packed: the word-aligned packed format (kid_classify_packed_host); e2e_text: the same
+         through kid_classify_host from bases + qualities (what round 1 reported as e2e)
   roofline.achieved = lookups/launch x 32 B / mean kid_classify3_kernel time (32 B = one DRAM sector
          per lookup); peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline: the CPU oracle (a port, oracle/kid_oracle.c) single-threaded on a bounded sample;
@@ -231,6 +232,23 @@ def bind_to_gpu_numa(local_rank: int):
 
 
 # ------------------------------------------------------------------------------------ ours
+def pack_dense_on_host(kid, np, hseq, hqual, n_reads, read_len, torch):
+    """kid_pack_reads_dense (the parser-side writer of dense batches) over the whole batch on ONE host thread,
+    into pinned memory; returns (DenseBatch, seconds).  Untimed setup: a parser does this per record."""
+    nbytes = n_reads * read_len
+    pin = lambda n: torch.empty(n, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    dense = kid.DenseBatch(n_reads, nbytes, codes=pin(int(kid.lib.kid_dense_bound(nbytes))), boff=pin(n_reads + 1),
+                           flagbits=pin(n_reads // 32 + 2), inv=pin(max(1024, nbytes // 100)))
+    seq, qual = hseq.numpy(), hqual.numpy()
+    step = 1 << 16
+    t0 = time.perf_counter()
+    for r0 in range(0, n_reads, step):
+        n = min(step, n_reads - r0)
+        off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len))
+        dense.append(seq[r0 * read_len:(r0 + n) * read_len], qual[r0 * read_len:(r0 + n) * read_len], off)
+    return dense, time.perf_counter() - t0
+
+
 def pack_on_host(kid, np, hseq, hqual, n_reads, read_len, hwords, hmeta):
     """kid_pack_reads (the parser-side writer of packed batches) over the whole batch on ONE host
     thread, slice by slice so that the words of consecutive slices follow each other; returns
@@ -379,7 +397,7 @@ def run_ours(args):
     gpu_taxa = dout.cpu().numpy()
 
     # ---- end to end through the host-buffer entry points
-    e2e = e2e_text = host_pack = None
+    e2e = e2e_text = e2e_packed = host_pack = None
     if not args.no_e2e:
         hseq = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
         hqual = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
@@ -422,8 +440,20 @@ def run_ours(args):
                 sample.classify_packed_host(hwords, hmeta, n_reads, hout)
                 return multi_gpu.finish(engine)
 
-            e2e = timed(step_packed)
-            e2e["input"] = "packed batch in pinned host memory (kid_pack_reads format), kid_classify_packed_host"
+            e2e_packed = timed(step_packed)
+            e2e_packed["input"] = "packed batch in pinned host memory (kid_pack_reads format), kid_classify_packed_host"
+            del hwords, hmeta
+            dense, dense_s = pack_dense_on_host(kid, np, hseq, hqual, n_reads, READ_LEN, torch)
+            host_pack["dense_reads_per_s_per_core"] = n_reads / dense_s
+            host_pack["dense_bytes_per_read"] = dense.wire_bytes / n_reads
+
+            def step_dense():
+                sample.begin(stream)
+                sample.classify_dense_host(dense, hout)
+                return multi_gpu.finish(engine)
+
+            e2e = timed(step_dense)
+            e2e["input"] = "dense batch in pinned host memory (kid_pack_reads_dense format), kid_classify_dense_host"
 
         def step_text():
             sample.begin(stream)
@@ -471,7 +501,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
-        "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e, "e2e_text": e2e_text,
+        "config": workload_config(args, wl.n_probes), "clocks": clk, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_text": e2e_text,
         "host_pack": host_pack,
         "gpu_launches": int(gpu_launches), "roofline": roofline,
         "lookups_per_s_whole_step": world * lookups / (ms_per_step / 1e3),

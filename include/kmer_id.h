@@ -188,6 +188,32 @@ int kid_classify_packed_device(kid_sample *s, const uint32_t *words, const uint3
 int kid_classify_packed_host(kid_sample *s, const uint32_t *words, uint32_t word0, const uint32_t *meta,
                              size_t n_reads, int32_t *out_taxon);
 
+/* ---- dense read batches: the fewest bytes on the wire ------------------------------------------
+ * 41.5 bytes per 150-base read instead of 50.6: no padding at all, one 32-bit offset per read, and the
+ * rare non-ACGT bases as a list of positions instead of validity words.
+ *   codes     uint32 stream of 2-bit codes, 16 per word, first base in the top bit pair; read r occupies
+ *             bases [boff[r], boff[r+1]) of the stream (its trimmed span; a dropped read has none).
+ *             codes[0] holds bases 16*(base0/16) .. of the stream (base0 = what kid_pack_reads_dense got).
+ *   boff      uint32[n_reads+1]
+ *   flagbits  bit (read0 + r) % 32 of word (read0 + r) / 32: read r contains a base outside ACGT
+ *   inv       uint32[n_inv]: stream positions of those bases, ascending
+ * kid_pack_reads_dense appends n_reads reads to a batch (base0 / read0 = bases / reads already in it; the
+ * arrays it is given start at the batch's beginning for flagbits, at the append position for the
+ * rest).  The device turns a dense batch into a packed one with one streaming kernel
+ * (kid_expand_kernel) before the scan.  Limits: < 2^32 bases per batch. */
+size_t kid_dense_bound(uint64_t bases); /* words of `codes` that `bases` bases need at most */
+int kid_pack_reads_dense(const uint8_t *seq, const uint8_t *qual, const uint64_t *off, size_t n_reads,
+                         unsigned flags, uint32_t base0, uint32_t *codes, size_t codes_cap, uint32_t *boff,
+                         uint32_t *flagbits, size_t read0, uint32_t *inv, size_t inv_cap, size_t *n_inv,
+                         uint32_t *span, uint32_t *n_bases);
+/* Host buffers, chunked over the slots, returns when out_taxon (host int32[n_reads] or NULL) is complete.
+ * kid_sample_set_chunk_reads values are rounded to multiples of 32 reads here. */
+int kid_classify_dense_host(kid_sample *s, const uint32_t *codes, const uint32_t *boff, const uint32_t *flagbits,
+                            const uint32_t *inv, size_t n_inv, size_t n_reads, int32_t *out_taxon);
+int kid_classify_dense_async(kid_sample *s, int slot, const uint32_t *codes, const uint32_t *boff,
+                             const uint32_t *flagbits, const uint32_t *inv, size_t n_inv, size_t n_reads,
+                             int32_t *out_taxon);
+
 /* ---- asynchronous slots -------------------------------------------------------------------------
  * One host thread pipelines parse | H2D | kernels | D2H: it fills a pinned buffer, submits it on a
  * slot and goes on parsing; kid_wait(slot) returns when that slot's outputs are complete and its

@@ -56,6 +56,11 @@ _SIGS = {
     "kid_pack_bound": (_sz, [_sz, _u64]),
     "kid_pack_reads": (_i, [_vp, _vp, _vp, _sz, _u, C.c_uint32, _vp, _sz, _vp, _vp, C.POINTER(_sz)]),
     "kid_pack_device": (_i, [_vp, _vp, _vp, _vp, _u64, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "kid_dense_bound": (_sz, [_u64]),
+    "kid_pack_reads_dense": (_i, [_vp, _vp, _vp, _sz, _u, C.c_uint32, _vp, _sz, _vp, _vp, _sz, _vp, _sz,
+                                  C.POINTER(_sz), _vp, C.POINTER(C.c_uint32)]),
+    "kid_classify_dense_host": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "kid_classify_dense_async": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     "kid_classify_packed_device": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "kid_classify_packed_host": (_i, [_vp, _vp, C.c_uint32, _vp, _sz, _vp]),
     "kid_classify_async": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
@@ -153,6 +158,47 @@ def pack_reads(seq: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray, fla
                               _np_ptr(span) if span is not None else None, C.byref(nw)))
     out = (words[:nw.value], meta[:2 * (n + 1)])
     return out + (span,) if want_span else out
+
+
+class DenseBatch:
+    """A dense read batch in host memory (include/kmer_id.h): filled by append(), handed to
+    Sample.classify_dense_host / classify_dense_async.  Arrays may be preallocated (pinned views)."""
+
+    def __init__(self, max_reads: int, max_bases: int, codes=None, boff=None, flagbits=None, inv=None,
+                 max_inv: Optional[int] = None, flags: int = 0):
+        self.flags = flags
+        self.codes = codes if codes is not None else np.zeros(int(lib.kid_dense_bound(max_bases)), np.uint32)
+        self.boff = boff if boff is not None else np.zeros(max_reads + 1, np.uint32)
+        self.flagbits = flagbits if flagbits is not None else np.zeros(max_reads // 32 + 2, np.uint32)
+        self.inv = inv if inv is not None else np.zeros(max_inv if max_inv is not None else max(1024, max_bases // 64), np.uint32)
+        self.n = 0
+        self.n_bases = 0
+        self.n_inv = 0
+        self.boff[0] = 0
+
+    def append(self, seq: np.ndarray, qual: Optional[np.ndarray], off: np.ndarray, want_span: bool = False):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = off.size - 1
+        if qual is not None:
+            qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        assert self.n + n + 1 <= self.boff.size
+        span = np.zeros((n, 2), dtype=np.uint32) if want_span else None
+        ni, nb = _sz(0), C.c_uint32(0)
+        w0 = self.n_bases >> 4
+        _check(lib.kid_pack_reads_dense(_np_ptr(seq), _np_ptr(qual) if qual is not None else None, _np_ptr(off), n,
+                                        self.flags, self.n_bases, self.codes[w0:].ctypes.data, self.codes.size - w0,
+                                        self.boff[self.n:].ctypes.data, _np_ptr(self.flagbits), self.n,
+                                        self.inv[self.n_inv:].ctypes.data, self.inv.size - self.n_inv, C.byref(ni),
+                                        _np_ptr(span) if span is not None else None, C.byref(nb)))
+        self.n += n
+        self.n_bases = nb.value
+        self.n_inv += ni.value
+        return span
+
+    @property
+    def wire_bytes(self) -> int:
+        return 4 * (((self.n_bases + 15) >> 4) + self.n + 1 + (self.n + 31) // 32 + self.n_inv)
 
 
 class Database:
@@ -255,6 +301,15 @@ class Sample:
     def classify_packed_host(self, words, meta, n_reads: int, out_taxon=None, word0: int = 0):
         """Packed batch in host memory; returns when out_taxon is complete."""
         _check(lib.kid_classify_packed_host(self._h, _as_ptr(words), word0, _as_ptr(meta), n_reads,
+                                            _as_ptr(out_taxon)))
+
+    def classify_dense_host(self, batch: "DenseBatch", out_taxon=None):
+        _check(lib.kid_classify_dense_host(self._h, _as_ptr(batch.codes), _as_ptr(batch.boff), _as_ptr(batch.flagbits),
+                                           _as_ptr(batch.inv), batch.n_inv, batch.n, _as_ptr(out_taxon)))
+
+    def classify_dense_async(self, slot: int, batch: "DenseBatch", out_taxon=None):
+        _check(lib.kid_classify_dense_async(self._h, slot, _as_ptr(batch.codes), _as_ptr(batch.boff),
+                                            _as_ptr(batch.flagbits), _as_ptr(batch.inv), batch.n_inv, batch.n,
                                             _as_ptr(out_taxon)))
 
     def classify_async(self, slot: int, seq, qual, off, n_reads: int, out_taxon=None, out_span=None):

@@ -62,6 +62,8 @@ struct HostSlot { // one asynchronous slot: a stream and its device staging buff
     uint32_t *out_span = nullptr;
     size_t cap_bytes = 0, cap_reads = 0, cap_words = 0;
     bool has_qual = false;
+    uint32_t *dn_codes = nullptr, *dn_boff = nullptr, *dn_flags = nullptr, *dn_inv = nullptr; // dense batches
+    size_t dn_cap_codes = 0, dn_cap_reads = 0, dn_cap_inv = 0;
 };
 
 } // namespace
@@ -475,6 +477,7 @@ void kid_sample_free(kid_sample *s)
         if (h.stream) { cudaStreamSynchronize(h.stream); cudaStreamDestroy(h.stream); }
         cudaFree(h.seq); cudaFree(h.qual); cudaFree(h.off); cudaFree(h.out_taxon); cudaFree(h.out_span);
         cudaFree(h.words); cudaFree(h.meta);
+        cudaFree(h.dn_codes); cudaFree(h.dn_boff); cudaFree(h.dn_flags); cudaFree(h.dn_inv);
     }
     cudaFree(s->dev.words); cudaFree(s->dev.meta);
     if (s->begin_ev) cudaEventDestroy(s->begin_ev);
@@ -761,6 +764,82 @@ static int submit_packed(kid_sample *s, HostSlot &h, const uint32_t *words, uint
 // chunk's kernel runs, the copies of the next ones keep the DMA engine busy
 static const int kHostSlots = getenv("KID_HOST_SLOTS") ? std::max(1, std::min(KID_MAX_SLOTS, atoi(getenv("KID_HOST_SLOTS")))) : 4; // measured: 2 -> 447, 3 -> 472, 4 -> 485 M pairs/s
 
+static int reserve_dense(HostSlot &h, size_t code_words, size_t reads, size_t n_inv)
+{
+    auto grow = [&](uint32_t *&p, size_t &cap, size_t need) -> int {
+        if (need <= cap && p) return KID_OK;
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t c = need + need / 4 + 64;
+        KID_CUDA(cudaMalloc(&p, sizeof(uint32_t) * c));
+        cap = c;
+        return KID_OK;
+    };
+    int rc = grow(h.dn_codes, h.dn_cap_codes, code_words + 8);
+    if (!rc) rc = grow(h.dn_inv, h.dn_cap_inv, n_inv + 1);
+    if (!rc && (reads + 1 > h.dn_cap_reads || !h.dn_boff)) {
+        if (h.stream) KID_CUDA(cudaStreamSynchronize(h.stream));
+        cudaFree(h.dn_boff); cudaFree(h.dn_flags);
+        h.dn_boff = h.dn_flags = nullptr;
+        h.dn_cap_reads = 0;
+        const size_t c = reads + reads / 4 + 64;
+        KID_CUDA(cudaMalloc(&h.dn_boff, sizeof(uint32_t) * (c + 1)));
+        KID_CUDA(cudaMalloc(&h.dn_flags, sizeof(uint32_t) * (c / 32 + 2)));
+        h.dn_cap_reads = c;
+    }
+    return rc;
+}
+
+// reads [r0, r0+n) of a host dense batch (r0 a multiple of 32): H2D, expand, scan, D2H on the slot's stream.
+// codes[0] holds the stream from position 16*(boff[0]/16) on; inv lists the batch's non-ACGT positions.
+static int submit_dense(kid_sample *s, HostSlot &h, const uint32_t *codes, const uint32_t *boff, const uint32_t *flagbits,
+                        const uint32_t *inv, size_t n_inv, size_t r0, size_t n, int32_t *out_taxon)
+{
+    const uint32_t origin = (boff[0] >> 4) << 4;          // stream position of codes[0]
+    const uint32_t ba = boff[r0], bb = boff[r0 + n];      // this chunk's bases
+    if (bb < ba || ba < origin) return fail(KID_EINVAL, "dense batch: base offsets must not decrease");
+    const uint32_t bias = (ba >> 4) << 4;
+    const size_t w0 = (bias - origin) >> 4, nw = ((size_t)(bb - bias) + 15) >> 4;
+    // this chunk's slice of the position list
+    const uint32_t *ia = inv, *ib = inv;
+    if (n_inv) {
+        ia = std::lower_bound(inv, inv + n_inv, ba);
+        ib = std::lower_bound(ia, inv + n_inv, bb);
+    }
+    const size_t ni = (size_t)(ib - ia);
+    const uint64_t bound = kid_pack_word_index((uint64_t)(bb - bias), n) + 2;
+    if (bound >= 0x80000000ull) return fail(KID_ERANGE, "dense batch: chunk too large");
+    int rc = slot_open(s, h);
+    if (!rc) rc = reserve_dense(h, nw, n, ni);
+    if (!rc) rc = reserve_packed(h, (size_t)bound, n);
+    if (rc) return rc;
+    if (nw) KID_CUDA(cudaMemcpyAsync(h.dn_codes, codes + w0, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, h.stream));
+    KID_CUDA(cudaMemcpyAsync(h.dn_boff, boff + r0, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, h.stream));
+    KID_CUDA(cudaMemcpyAsync(h.dn_flags, flagbits + r0 / 32, sizeof(uint32_t) * ((n + 31) / 32), cudaMemcpyHostToDevice, h.stream));
+    if (ni) KID_CUDA(cudaMemcpyAsync(h.dn_inv, ia, sizeof(uint32_t) * ni, cudaMemcpyHostToDevice, h.stream));
+    __atomic_fetch_add(&s->h2d, sizeof(uint32_t) * (nw + n + 1 + (n + 31) / 32 + ni), __ATOMIC_RELAXED);
+    KidExpandParams ep;
+    ep.codes = h.dn_codes;
+    ep.boff = h.dn_boff;
+    ep.bias = bias;
+    ep.flagbits = h.dn_flags;
+    ep.inv = h.dn_inv;
+    ep.n_inv = (uint32_t)ni;
+    ep.n_reads = n;
+    ep.words = h.words;
+    ep.meta = h.meta;
+    KID_CUDA(kid_launch_expand(ep, s->db->sm_count, h.stream));
+    KidPackedParams p = make_packed_params(s, h.words, h.meta, 0, n, out_taxon ? h.out_taxon : nullptr);
+    KID_CUDA(kid_launch_classify3(p, s->db->sm_count, h.stream));
+    if (out_taxon) {
+        KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
+        __atomic_fetch_add(&s->d2h, sizeof(int32_t) * n, __ATOMIC_RELAXED);
+    }
+    return KID_OK;
+}
+
 static int sync_slots(kid_sample *s)
 {
     for (HostSlot &h : s->slot)
@@ -801,6 +880,37 @@ int kid_classify_packed_host(kid_sample *s, const uint32_t *words, uint32_t word
         if (rc) { sync_slots(s); return rc; }
     }
     return sync_slots(s);
+}
+
+int kid_classify_dense_host(kid_sample *s, const uint32_t *codes, const uint32_t *boff, const uint32_t *flagbits,
+                            const uint32_t *inv, size_t n_inv, size_t n_reads, int32_t *out_taxon)
+{
+    if (!s) return fail(KID_EINVAL, "kid_classify_dense_host: s is NULL");
+    if (n_reads == 0) return KID_OK;
+    if (!codes || !boff || !flagbits || (n_inv && !inv)) return fail(KID_EINVAL, "kid_classify_dense_host: NULL argument");
+    if (s->db->layout != KID_LAYOUT_MINIMIZER)
+        return fail(KID_EINVAL, "dense batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
+    DeviceGuard guard(s->db->device);
+    const size_t chunk = std::max<size_t>(32, s->chunk_reads & ~(size_t)31); // flag words must not straddle chunks
+    int k = 0;
+    for (size_t r0 = 0; r0 < n_reads; r0 += chunk, k = (k + 1) % kHostSlots) {
+        const size_t n = (n_reads - r0 < chunk) ? n_reads - r0 : chunk;
+        int rc = submit_dense(s, s->slot[k], codes, boff, flagbits, inv, n_inv, r0, n, out_taxon);
+        if (rc) { sync_slots(s); return rc; }
+    }
+    return sync_slots(s);
+}
+
+int kid_classify_dense_async(kid_sample *s, int slot, const uint32_t *codes, const uint32_t *boff, const uint32_t *flagbits,
+                             const uint32_t *inv, size_t n_inv, size_t n_reads, int32_t *out_taxon)
+{
+    if (!s || slot < 0 || slot >= KID_MAX_SLOTS) return fail(KID_EINVAL, "kid_classify_dense_async: bad sample or slot");
+    if (n_reads == 0) return KID_OK;
+    if (!codes || !boff || !flagbits || (n_inv && !inv)) return fail(KID_EINVAL, "kid_classify_dense_async: NULL argument");
+    if (s->db->layout != KID_LAYOUT_MINIMIZER)
+        return fail(KID_EINVAL, "dense batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
+    DeviceGuard guard(s->db->device);
+    return submit_dense(s, s->slot[slot], codes, boff, flagbits, inv, n_inv, 0, n_reads, out_taxon);
 }
 
 int kid_classify_async(kid_sample *s, int slot, const uint8_t *seq, const uint8_t *qual, const uint64_t *off,

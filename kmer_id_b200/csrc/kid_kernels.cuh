@@ -76,6 +76,20 @@ __host__ __device__ __forceinline__ uint64_t kid_pack_word_index(uint64_t rel_of
 }
 cudaError_t kid_launch_pack(const KidPackParams &p, int sm_count, cudaStream_t stream);
 
+// dense batch (include/kmer_id.h) -> packed batch, same word placement as kid_pack_kernel
+struct KidExpandParams {
+    const uint32_t *codes;    // codes[0] = the 16 bases from stream position `bias` on
+    const uint32_t *boff;     // n_reads + 1 stream positions
+    uint32_t bias;            // multiple of 16
+    const uint32_t *flagbits; // bit r % 32 of word r / 32 (r = 0 is this batch's first read)
+    const uint32_t *inv;      // stream positions of the non-ACGT bases of these reads, ascending
+    uint32_t n_inv;
+    size_t n_reads;
+    uint32_t *words;
+    uint2 *meta; // n_reads + 1
+};
+cudaError_t kid_launch_expand(const KidExpandParams &p, int sm_count, cudaStream_t stream);
+
 // every kernel launch of this library bumps this (bench.py reports it as gpu_launches)
 extern unsigned long long g_kid_kernel_launches;
 #define KID_COUNT_LAUNCH() (__atomic_add_fetch(&g_kid_kernel_launches, 1ULL, __ATOMIC_RELAXED))

@@ -167,6 +167,95 @@ kid_pack_kernel(const KidPackParams p)
     }
 }
 
+// ---- dense batch -> packed batch ----------------------------------------------------------------
+// What arrives over PCIe from a host parser is the dense form (no padding, offsets only, non-ACGT bases
+// as a position list); the scan wants every read on a word boundary with validity words.  Same shape as
+// the PACK phase above: a warp takes 32 reads, one lane per 32 bases; the source is already 2-bit codes,
+// so a unit is three words and two funnel shifts.
+struct ExpandTile {
+    uint32_t b0[32];  // first base of the read, relative to the batch's codes
+    uint32_t pre[33]; // units before read i
+    uint32_t tlen[32];
+};
+
+__global__ void __launch_bounds__(kPackThreads)
+kid_expand_kernel(const KidExpandParams p)
+{
+    __shared__ ExpandTile tiles[kPackThreads / 32];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    ExpandTile &t = tiles[threadIdx.x >> 5];
+    const size_t n_tiles = (p.n_reads + 31) / 32;
+    const size_t warps_total = (size_t)gridDim.x * (kPackThreads / 32);
+    for (size_t tile = (size_t)blockIdx.x * (kPackThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+        const size_t r = tile * 32 + (size_t)lane;
+        const bool have = r < p.n_reads;
+        uint32_t b0 = 0, tl = 0;
+        if (have) {
+            const uint32_t a = __ldg(p.boff + r);
+            tl = __ldg(p.boff + r + 1) - a;
+            b0 = a - p.bias;
+        }
+        const uint32_t fw = __ldg(p.flagbits + tile); // the flags of this tile's 32 reads
+        const uint32_t units = (tl + 31u) >> 5;
+        uint32_t incl = units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += v;
+        }
+        __syncwarp();
+        t.b0[lane] = b0;
+        t.tlen[lane] = tl;
+        t.pre[lane + 1] = incl;
+        if (lane == 0) t.pre[0] = 0;
+        __syncwarp();
+        const uint32_t total = t.pre[32];
+        for (uint32_t w = lane; w < total; w += 32) {
+            int ri = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1)
+                if (t.pre[ri + step] <= w) ri += step;
+            const uint32_t u = w - t.pre[ri];
+            const uint32_t tlr = t.tlen[ri], rb = t.b0[ri];
+            const int nb = min(32, (int)(tlr - 32u * u));
+            const uint32_t sb = rb + 32u * u; // first base of this unit in the codes
+            const uint32_t *src = p.codes + (sb >> 4);
+            const int sh = (int)(sb & 15u) * 2;
+            const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+            uint32_t c0 = __funnelshift_l(a1, a0, sh), c1 = __funnelshift_l(a2, a1, sh);
+            if (nb < 16) c0 &= 0xFFFFFFFFu << (2 * (16 - nb));
+            if (nb < 32) c1 = nb > 16 ? c1 & (0xFFFFFFFFu << (2 * (32 - nb))) : 0u;
+            uint32_t valid = nb >= 32 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (32 - nb);
+            const bool flagged = (fw >> ri) & 1u;
+            if (flagged && p.n_inv) { // clear the bits of the listed positions that fall into this unit
+                const uint32_t lo = sb + p.bias, hi = lo + (uint32_t)nb; // stream positions [lo, hi)
+                uint32_t a = 0, b = p.n_inv; // first entry >= lo
+                while (a < b) {
+                    const uint32_t m = (a + b) >> 1;
+                    if (__ldg(p.inv + m) < lo) a = m + 1; else b = m;
+                }
+                for (; a < p.n_inv; a++) {
+                    const uint32_t pos = __ldg(p.inv + a);
+                    if (pos >= hi) break;
+                    valid &= ~(0x80000000u >> (pos - lo));
+                }
+            }
+            const uint32_t wf = (uint32_t)kid_pack_word_index(rb, tile * 32 + (size_t)ri);
+            const uint32_t cwn = (tlr + 15u) >> 4;
+            p.words[wf + 2 * u] = c0;
+            if (2 * u + 1 < cwn) p.words[wf + 2 * u + 1] = c1;
+            p.words[wf + cwn + u] = valid;
+        }
+        if (have) p.meta[r] = make_uint2((uint32_t)kid_pack_word_index(b0, r) | (((fw >> lane) & 1u) ? KID_PK_FLAG : 0u), tl);
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t total = __ldg(p.boff + p.n_reads) - p.bias;
+        p.meta[p.n_reads] = make_uint2((uint32_t)kid_pack_word_index(total, p.n_reads), 0u);
+    }
+}
+
 } // namespace
 
 cudaError_t kid_launch_pack(const KidPackParams &p, int sm_count, cudaStream_t stream)
@@ -178,6 +267,18 @@ cudaError_t kid_launch_pack(const KidPackParams &p, int sm_count, cudaStream_t s
     if (blocks > cap) blocks = cap;
     if (p.qual) kid_pack_kernel<true><<<(unsigned)blocks, kPackThreads, 0, stream>>>(p);
     else kid_pack_kernel<false><<<(unsigned)blocks, kPackThreads, 0, stream>>>(p);
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t kid_launch_expand(const KidExpandParams &p, int sm_count, cudaStream_t stream)
+{
+    if (p.n_reads == 0) return cudaSuccess;
+    const size_t warps = (p.n_reads + 31) / 32;
+    size_t blocks = (warps + kPackThreads / 32 - 1) / (kPackThreads / 32);
+    const size_t cap = (size_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    kid_expand_kernel<<<(unsigned)blocks, kPackThreads, 0, stream>>>(p);
     KID_COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -223,4 +223,80 @@ int kid_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *off,
     return KID_OK;
 }
 
+size_t kid_dense_bound(uint64_t bases) { return (size_t)((bases + 15) / 16) + 4; }
+
+int kid_pack_reads_dense(const uint8_t *seq, const uint8_t *qual, const uint64_t *off, size_t n_reads, unsigned flags,
+                         uint32_t base0, uint32_t *codes, size_t codes_cap, uint32_t *boff, uint32_t *flagbits,
+                         size_t read0, uint32_t *inv, size_t inv_cap, size_t *n_inv, uint32_t *span, uint32_t *n_bases)
+{
+    if (!boff || !flagbits || !n_inv || !n_bases || (n_reads && (!seq || !off || !codes))) return KID_EINVAL;
+    const pack32_fn pack32 = choose_packer(flags);
+    const bool accept_u = (flags & KID_DB_ACCEPT_U) != 0;
+    // `codes` holds the stream from the 16-base unit that contains base0 on: word i = bases 16*(base0/16 + i) ...
+    const uint64_t origin = (uint64_t)(base0 >> 4) << 4;
+    uint64_t b = base0; // next free base
+    size_t ni = 0;
+    if ((b & 15) == 0 && codes_cap) codes[(b - origin) >> 4] = 0; // a word that is only partly ours is OR-ed into
+    for (size_t r = 0; r < n_reads; r++) {
+        const uint64_t o = off[r];
+        const uint64_t len64 = off[r + 1] - o;
+        if (len64 > 0x7FFFFFFFull) return KID_EINVAL; // one read < 2^31 bases
+        const int len = (int)len64;
+        int start = 0, stop = len - 1;
+        if (qual) trim_span(reinterpret_cast<const signed char *>(qual) + o, len, start, stop);
+        if (span) { span[2 * r] = (uint32_t)start; span[2 * r + 1] = (uint32_t)stop; }
+        const int tlen = stop - start + 1;
+        const size_t gr = read0 + r; // position of this read's flag bit
+        if ((gr & 31) == 0) flagbits[gr >> 5] = 0;
+        boff[r] = (uint32_t)b;
+        if (tlen <= KID_KSIZE) continue; // :755 - the read vanishes: no bases
+        if (b + (uint64_t)tlen >= 0xFFFFFFF0ull) return KID_ERANGE; // base offsets are 32-bit: split the batch
+        if (((b + (uint64_t)tlen - origin + 15) >> 4) + 3 > codes_cap) return KID_ENOMEM;
+        const uint8_t *src = seq + o + (uint64_t)start;
+        bool flagged = false;
+        for (int k = 0; k < tlen; k += 32) {
+            const int rem = tlen - k < 32 ? tlen - k : 32;
+            Packed32 pk;
+            if (rem == 32) {
+                pk = pack32(src + k, accept_u);
+            } else { // the tail goes through a padded copy: nothing is read past the read's last base
+                uint8_t tmp[32];
+                memset(tmp, 0, sizeof tmp);
+                memcpy(tmp, src + k, (size_t)rem);
+                pk = pack32(tmp, accept_u);
+            }
+            // append 64 bits (32 bases; those past rem are 0) at base b: bit 2*(b%16) of word (b - origin)/16, MSB first
+            const uint64_t v = ((uint64_t)pk.c0 << 32) | pk.c1;
+            const size_t w = (size_t)((b - origin) >> 4);
+            const unsigned sh = (unsigned)(b & 15) * 2;
+            if (sh == 0) {
+                codes[w] = (uint32_t)(v >> 32);
+                codes[w + 1] = (uint32_t)v;
+                codes[w + 2] = 0;
+            } else {
+                codes[w] |= (uint32_t)(v >> (32 + sh));
+                codes[w + 1] = (uint32_t)(v >> sh);
+                codes[w + 2] = (uint32_t)(v << (32 - sh));
+            }
+            const uint32_t want = rem == 32 ? 0xFFFFFFFFu : ~0u << (32 - rem);
+            uint32_t bad = ~pk.valid & want;
+            if (bad) {
+                flagged = true;
+                while (bad) { // positions of the bases that are not ACGT(+U), ascending
+                    const int i = __builtin_clz(bad);
+                    bad &= ~(0x80000000u >> i);
+                    if (ni >= inv_cap) return KID_ENOMEM;
+                    inv[ni++] = (uint32_t)(b + (uint64_t)i);
+                }
+            }
+            b += (uint64_t)rem;
+        }
+        if (flagged) flagbits[gr >> 5] |= 1u << (gr & 31);
+    }
+    boff[n_reads] = (uint32_t)b;
+    *n_inv = ni;
+    *n_bases = (uint32_t)b;
+    return KID_OK;
+}
+
 } // extern "C"

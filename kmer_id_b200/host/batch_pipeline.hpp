@@ -1,5 +1,5 @@
-// batch_pipeline.hpp - one host thread keeps packed batches in flight on one or several kid_sample
-// objects (kid_classify_packed_async / kid_wait) and hands every finished batch to `done` in stream
+// batch_pipeline.hpp - one host thread keeps dense batches in flight on one or several kid_sample
+// objects (kid_classify_dense_async / kid_wait) and hands every finished batch to `done` in stream
 // order.  While the GPUs work the reader's threads parse and pack the next batches and this thread
 // post-processes the previous one.  Replaces the synchronous per-record call of the reference
 // (process_fqgz -> process_qual, newkmer_10nx.cpp:798-801).
@@ -46,7 +46,7 @@ void classify_stream(kid_sample *const *smps, int n_smps, int slot_base, ReadBat
             kid_sample *smp = smps[submitted % (size_t)n_smps];
             b->slot = slot_base + (int)((submitted / (size_t)n_smps) % kPipelineSlots);
             submitted++;
-            if (kid_classify_packed_async(smp, b->slot, b->words, 0, b->meta, b->n, b->taxon) != 0) {
+            if (kid_classify_dense_async(smp, b->slot, b->codes, b->boff, b->flagbits, b->inv, b->n_inv, b->n, b->taxon) != 0) {
                 fprintf(stderr, "kmer_id_b200: %s\n", kid_last_error());
                 exit(1);
             }

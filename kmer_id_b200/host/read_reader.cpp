@@ -45,7 +45,8 @@ void pinned_put(void *p, size_t bytes)
     std::lock_guard<std::mutex> lk(g_pinned_mu);
     g_pinned_free.emplace_back(p, bytes);
 }
-size_t batch_words(size_t max_reads, size_t cap_bytes) { return kid_pack_bound(max_reads, cap_bytes) + 16; }
+size_t batch_code_words(size_t cap_bytes) { return kid_dense_bound(cap_bytes) + 16; }
+size_t batch_inv_cap(size_t cap_bytes) { return cap_bytes / 16 + 4096; } // non-ACGT bases are rare; pack_record grows the list
 
 // text bytes per super-block of the parallel gz FASTQ path
 size_t parallel_block_bytes(size_t max_bytes) { return std::max<size_t>(4096, std::min<size_t>(max_bytes, (size_t)8 << 20)); }
@@ -61,11 +62,10 @@ int pipeline_depth(int slots) { return slots + 3 + (int)parse_threads_default();
 
 void prewarm_batch_buffers(size_t max_reads, size_t max_bytes, int readers, int depth)
 {
-    const size_t wbytes = 4 * batch_words(max_reads, max_bytes + kRefLineLimit);
-    const size_t mbytes = 8 * (max_reads + 1), tbytes = 4 * max_reads;
+    const size_t cap = max_bytes + kRefLineLimit;
     std::vector<std::pair<void *, size_t>> got;
     for (int i = 0; i < readers * depth; i++)
-        for (size_t bytes : { wbytes, mbytes, tbytes }) {
+        for (size_t bytes : { 4 * batch_code_words(cap), 4 * (max_reads + 1), 4 * (max_reads / 32 + 2), 4 * batch_inv_cap(cap), 4 * max_reads }) {
             void *p = nullptr;
             if (kid_host_alloc(&p, bytes) != 0) break; // the reader reports the failure when it needs the buffer
             got.emplace_back(p, bytes);
@@ -84,9 +84,11 @@ void ReadBatchReader::alloc_batch(ReadBatch &b, size_t cap_bytes, size_t cap_rea
     }
     b.seq = (uint8_t *)malloc(cap_bytes + 16);
     if (!b.seq) { fprintf(stderr, "kmer_id_b200: out of memory for a %zu-byte batch\n", cap_bytes); exit(1); }
-    b.cap_words = batch_words(cap_reads, cap_bytes);
-    b.words = (uint32_t *)pinned_get(4 * b.cap_words);
-    b.meta = (uint32_t *)pinned_get(8 * (cap_reads + 1));
+    b.codes = (uint32_t *)pinned_get(4 * batch_code_words(cap_bytes));
+    b.boff = (uint32_t *)pinned_get(4 * (cap_reads + 1));
+    b.flagbits = (uint32_t *)pinned_get(4 * (cap_reads / 32 + 2));
+    b.cap_inv = batch_inv_cap(cap_bytes);
+    b.inv = (uint32_t *)pinned_get(4 * b.cap_inv);
     b.taxon = (int32_t *)pinned_get(4 * cap_reads);
 }
 
@@ -97,12 +99,14 @@ void ReadBatchReader::free_batch(ReadBatch &b)
         pinned_put(b.qual, b.cap_bytes + 16);
     } else {
         free(b.seq);
-        pinned_put(b.words, 4 * b.cap_words);
-        pinned_put(b.meta, 8 * (b.cap_reads + 1));
+        pinned_put(b.codes, 4 * batch_code_words(b.cap_bytes));
+        pinned_put(b.boff, 4 * (b.cap_reads + 1));
+        pinned_put(b.flagbits, 4 * (b.cap_reads / 32 + 2));
+        pinned_put(b.inv, 4 * b.cap_inv);
         pinned_put(b.taxon, 4 * b.cap_reads);
     }
     b.seq = b.qual = nullptr;
-    b.words = b.meta = nullptr;
+    b.codes = b.boff = b.flagbits = b.inv = nullptr;
     b.taxon = nullptr;
 }
 
@@ -151,7 +155,9 @@ ReadBatch *ReadBatchReader::get_free()
     ReadBatch *b = free_.front();
     free_.pop_front();
     b->n = 0;
-    b->n_words = 0;
+    b->n_inv = 0;
+    b->n_bases = 0;
+    if (b->boff) b->boff[0] = 0;
     b->slot = -1;
     b->span.clear();
     b->off.assign(1, 0);
@@ -188,25 +194,42 @@ void ReadBatchReader::recycle(ReadBatch *b)
     cv_.notify_all();
 }
 
+// trim + pack one record onto the end of a batch's dense arrays (include/kmer_id.h); the caller has
+// made sure that bases and reads fit
+void ReadBatchReader::pack_record(ReadBatch &b, const char *seq, size_t seqlen, const char *qual)
+{
+    if (b.n_inv + seqlen > b.cap_inv) { // a record that could overflow the position list (N-rich data): grow it
+        const size_t cap = std::max(b.cap_inv * 2, b.n_inv + seqlen + 4096);
+        uint32_t *bigger = (uint32_t *)pinned_get(4 * cap);
+        memcpy(bigger, b.inv, 4 * b.n_inv);
+        pinned_put(b.inv, 4 * b.cap_inv);
+        b.inv = bigger;
+        b.cap_inv = cap;
+    }
+    const uint64_t one[2] = { 0, (uint64_t)seqlen };
+    uint32_t sp[2], nb = 0;
+    size_t ni = 0;
+    const size_t w0 = b.n_bases >> 4;
+    const int rc = kid_pack_reads_dense((const uint8_t *)seq, (const uint8_t *)qual, one, 1, pack_flags_, b.n_bases,
+                                        b.codes + w0, batch_code_words(b.cap_bytes) - w0, b.boff + b.n, b.flagbits, b.n,
+                                        b.inv + b.n_inv, b.cap_inv - b.n_inv, &ni, sp, &nb);
+    if (rc != 0) { fprintf(stderr, "kmer_id_b200: kid_pack_reads_dense failed (%d)\n", rc); exit(1); }
+    b.n_bases = nb;
+    b.n_inv += ni;
+    b.span.push_back(sp[0]);
+    b.span.push_back(sp[1]);
+}
+
 // one record into a batch that is known to have room (parallel gz FASTQ: sized per super-block)
 void ReadBatchReader::emit_into(ReadBatch &b, const char *acc, size_t acclen, const char *seq, size_t seqlen, const char *qual)
 {
-    const size_t need_words = (seqlen + 15) / 16 + (seqlen + 31) / 32 + 2;
-    if (b.off.back() + seqlen > b.cap_bytes || b.n >= b.cap_reads || b.n_words + need_words > b.cap_words) {
+    if (b.off.back() + seqlen > b.cap_bytes || b.n >= b.cap_reads) {
         fprintf(stderr, "kmer_id_b200: internal error: a super-block outgrew its batch\n");
         exit(1);
     }
     const uint64_t o = b.off.back();
     memcpy(b.seq + o, seq, seqlen);
-    const uint64_t one[2] = { 0, (uint64_t)seqlen };
-    uint32_t sp[2];
-    size_t nw = 0;
-    const int rc = kid_pack_reads((const uint8_t *)seq, (const uint8_t *)qual, one, 1, pack_flags_, (uint32_t)b.n_words,
-                                  b.words + b.n_words, b.cap_words - b.n_words, b.meta + 2 * b.n, sp, &nw);
-    if (rc != 0) { fprintf(stderr, "kmer_id_b200: kid_pack_reads failed (%d)\n", rc); exit(1); }
-    b.n_words += nw;
-    b.span.push_back(sp[0]);
-    b.span.push_back(sp[1]);
+    pack_record(b, seq, seqlen, qual);
     b.off.push_back(o + seqlen);
     b.names.insert(b.names.end(), acc, acc + acclen);
     b.name_off.push_back((uint32_t)b.names.size());
@@ -218,8 +241,7 @@ void ReadBatchReader::emit(const char *acc, size_t acclen, const char *seq, size
 {
     ReadBatch *b = cur_;
     const bool packed = mode_ == BatchMode::Packed;
-    const size_t need_words = packed ? (seqlen + 15) / 16 + (seqlen + 31) / 32 + 2 : 0;
-    if (b->off.back() + seqlen > b->cap_bytes || b->n >= max_reads_ || b->n_words + need_words > b->cap_words) {
+    if (b->off.back() + seqlen > b->cap_bytes || b->n >= b->cap_reads) {
         if (b->n) {
             publish(b);
             b = cur_ = get_free();
@@ -227,23 +249,13 @@ void ReadBatchReader::emit(const char *acc, size_t acclen, const char *seq, size
         if (seqlen > b->cap_bytes) { // a record longer than a whole batch (a contig): this buffer grows for it
             free_batch(*b);
             alloc_batch(*b, seqlen + kRefLineLimit, max_reads_);
+            b->boff[0] = 0;
         }
     }
     const uint64_t o = b->off.back();
     memcpy(b->seq + o, seq, seqlen);
-    if (packed) {
-        const uint64_t one[2] = { 0, (uint64_t)seqlen };
-        uint32_t sp[2];
-        size_t nw = 0;
-        const int rc = kid_pack_reads((const uint8_t *)seq, (const uint8_t *)qual, one, 1, pack_flags_, (uint32_t)b->n_words,
-                                      b->words + b->n_words, b->cap_words - b->n_words, b->meta + 2 * b->n, sp, &nw);
-        if (rc != 0) { fprintf(stderr, "kmer_id_b200: kid_pack_reads failed (%d)\n", rc); exit(1); }
-        b->n_words += nw;
-        b->span.push_back(sp[0]);
-        b->span.push_back(sp[1]);
-    } else if (qual) {
-        memcpy(b->qual + o, qual, seqlen);
-    }
+    if (packed) pack_record(*b, seq, seqlen, qual);
+    else if (qual) memcpy(b->qual + o, qual, seqlen);
     b->off.push_back(o + seqlen);
     b->names.insert(b->names.end(), acc, acc + acclen);
     b->name_off.push_back((uint32_t)b->names.size());

@@ -21,9 +21,10 @@ namespace kidhost {
 enum class ReadFormat { GzFastq, PlainFastq, GzFasta, PlainFasta };
 
 // What a batch carries for the GPU.
-//   Packed (the hosts): every record is trimmed and 2-bit packed by kid_pack_reads while its lines are
-//           still in cache; words/meta/taxon are pinned and go to kid_classify_packed_async as they
-//           are.  Qualities are never copied; the bases are kept in ordinary memory for _reads.txt.
+//   Packed (the hosts): every record is trimmed and 2-bit packed by kid_pack_reads_dense while its lines
+//           are still in cache; codes/boff/flagbits/inv/taxon are pinned and go to
+//           kid_classify_dense_async as they are (41.5 bytes per 150-base read).  Qualities are never
+//           copied; the bases are kept in ordinary memory for _reads.txt.
 //   Text    (tests, and callers of kid_classify_host): bases and qualities in pinned buffers.
 enum class BatchMode { Packed, Text };
 
@@ -32,15 +33,19 @@ struct ReadBatch {
     uint8_t *seq = nullptr;   // cap_bytes + 16 (pinned in Text mode)
     uint8_t *qual = nullptr;  // Text mode, FASTQ: pinned, same offsets as seq (only the first seqlen
                               // bytes of a quality line are ever looked at, :724-753)
-    uint32_t *words = nullptr; // Packed mode: pinned, n_words used of cap_words (include/kmer_id.h)
-    uint32_t *meta = nullptr;  // Packed mode: pinned, 2 * (n + 1) used
-    int32_t *taxon = nullptr;  // Packed mode: pinned, cap_reads: where the GPU's per-read result lands
+    // Packed mode: the dense batch of include/kmer_id.h, all pinned
+    uint32_t *codes = nullptr;    // 2-bit stream, n_bases used of cap_bytes
+    uint32_t *boff = nullptr;     // n + 1 stream positions
+    uint32_t *flagbits = nullptr; // one bit per read
+    uint32_t *inv = nullptr;      // n_inv positions of non-ACGT bases, cap_inv
+    int32_t *taxon = nullptr;     // cap_reads: where the GPU's per-read result lands
     std::vector<uint32_t> span;     // Packed mode: 2n, (start, stop) as process_qual leaves them
     std::vector<uint64_t> off;      // n + 1
     std::vector<char> names;        // header lines as the reference keeps them, concatenated
     std::vector<uint32_t> name_off; // n + 1
-    size_t n = 0, n_words = 0;
-    size_t cap_bytes = 0, cap_words = 0, cap_reads = 0;
+    size_t n = 0, n_inv = 0;
+    uint32_t n_bases = 0;
+    size_t cap_bytes = 0, cap_inv = 0, cap_reads = 0;
     bool has_qual = true;
     bool last = false;        // no more batches after this one
     int slot = -1;            // for the consumer: the asynchronous slot this batch was submitted on
@@ -80,6 +85,7 @@ private:
     void publish(ReadBatch *b);
     void alloc_batch(ReadBatch &b, size_t cap_bytes, size_t cap_reads);
     void free_batch(ReadBatch &b);
+    void pack_record(ReadBatch &b, const char *seq, size_t seqlen, const char *qual);
     void run_gz_fastq_parallel(const std::string &path);
     void publish_ordered(uint64_t index, ReadBatch *b);
 

@@ -10,6 +10,7 @@
 #include "../../kmer_id_b200/host/db_loader.hpp"
 #include "../../kmer_id_b200/host/read_reader.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <ctime>
 #include <cstdio>
@@ -68,16 +69,18 @@ int main(int argc, char **argv)
         ReadBatchReader reader(fmt, argv[3], 7, 4096, 2, 0, BatchMode::Packed, argc > 4 ? (unsigned)atoi(argv[4]) : 0u);
         for (;;) {
             ReadBatch *b = reader.next();
-            if (b->n && (b->meta[2 * b->n] & 0x7FFFFFFFu) != b->n_words) { printf("BAD_END\n"); return 1; }
+            if (b->n && b->boff[b->n] != b->n_bases) { printf("BAD_END\n"); return 1; }
             for (size_t r = 0; r < b->n; r++) {
                 fwrite(b->names.data() + b->name_off[r], 1, b->name_off[r + 1] - b->name_off[r], stdout);
-                const uint32_t w0 = b->meta[2 * r] & 0x7FFFFFFFu, flagged = b->meta[2 * r] >> 31, tlen = b->meta[2 * r + 1];
+                const uint32_t a = b->boff[r], tlen = b->boff[r + 1] - a, flagged = (b->flagbits[r >> 5] >> (r & 31)) & 1u;
                 printf("\t%d\t%d\t%u\t%u\t", (int)b->span[2 * r], (int)b->span[2 * r + 1], tlen, flagged);
-                const uint32_t cw = (tlen + 15) / 16;
+                const uint32_t *ia = std::lower_bound(b->inv, b->inv + b->n_inv, a);
                 for (uint32_t i = 0; i < tlen; i++) {
-                    const uint32_t c = (b->words[w0 + i / 16] >> (30 - 2 * (i % 16))) & 3u;
-                    const uint32_t v = flagged ? (b->words[w0 + cw + i / 32] >> (31 - i % 32)) & 1u : 1u;
-                    fputc(v ? "ACGT"[c] : 'N', stdout);
+                    const uint32_t pos = a + i;
+                    const uint32_t c = (b->codes[pos >> 4] >> (30 - 2 * (pos & 15))) & 3u;
+                    bool bad = false;
+                    if (ia < b->inv + b->n_inv && *ia == pos) { bad = true; ia++; }
+                    fputc(bad ? 'N' : "ACGT"[c], stdout);
                 }
                 fputc('\n', stdout);
             }

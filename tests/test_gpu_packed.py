@@ -203,3 +203,58 @@ def test_more_taxa_than_the_shared_histogram_holds():
     assert np.array_equal(out, fin_o)
     _check_counts(gs, osamp)
     assert (fin_o > 24_576).sum() > 100
+
+
+@pytest.mark.parametrize("seed,n,kw", CASES)
+def test_dense_classify_matches_oracle(seed, n, kw):
+    """Dense batches (what the hosts ship: no padding, offsets only, non-ACGT positions as a list) through
+    kid_expand_kernel + the scan: bit-exact against the oracle, whole and in chunks of 32 / 1024 reads."""
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(seed + 100)
+    db = H.make_db(rng, 30000, n_dup=500, n_zero=50)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batch = H.make_reads(rng, db, n, **kw)
+    fin_o, _ = osamp.classify(batch.seq, batch.qual, batch.off)
+    dense = kid.DenseBatch(batch.n, int(batch.off[-1]), max_inv=int(batch.off[-1]))
+    half = batch.n // 3
+    for a, b in ((0, half), (half, batch.n)):  # appended in two calls
+        lo, hi = int(batch.off[a]), int(batch.off[b])
+        dense.append(batch.seq[lo:hi], batch.qual[lo:hi], batch.off[a:b + 1] - batch.off[a])
+    out = np.full(batch.n, -2, np.int32)
+    gs.classify_dense_host(dense, out)
+    bad = np.flatnonzero(out != fin_o)
+    assert bad.size == 0, f"{bad.size} reads differ, first {bad[:5]}: oracle {fin_o[bad[:5]]} gpu {out[bad[:5]]}"
+    _check_counts(gs, osamp)
+    for chunk in (32, 1024):
+        gs.set_chunk_reads(chunk)
+        out2 = np.full(batch.n, -2, np.int32)
+        gs.classify_dense_host(dense, out2)
+        osamp.classify(batch.seq, batch.qual, batch.off)
+        assert np.array_equal(out2, fin_o)
+        _check_counts(gs, osamp)
+
+
+def test_dense_async_slots():
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(35)
+    db = H.make_db(rng, 20000)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    batches = [H.make_reads(rng, db, 500 + 77 * i, n_rate=0.003, ragged=(i % 2 == 0)) for i in range(7)]
+    want = [osamp.classify(b.seq, b.qual, b.off)[0] for b in batches]
+    outs = [np.full(b.n, -2, np.int32) for b in batches]
+    held = {}
+    for i, b in enumerate(batches):
+        slot = i % kid.KID_MAX_SLOTS
+        if slot in held:
+            gs.wait(slot)
+        d = kid.DenseBatch(b.n, int(b.off[-1]), max_inv=int(b.off[-1]))
+        d.append(b.seq, b.qual, b.off)
+        held[slot] = d
+        gs.classify_dense_async(slot, d, outs[i])
+    for slot in range(kid.KID_MAX_SLOTS):
+        gs.wait(slot)
+    for i in range(len(batches)):
+        assert np.array_equal(outs[i], want[i]), i
+    _check_counts(gs, osamp)

@@ -138,3 +138,71 @@ def test_pack_errors_and_bound():
     # n_reads = 0 still writes the end entry
     rc = kid.lib.kid_pack_reads(None, None, None, 0, 0, 7, None, 0, meta.ctypes.data, None, C.byref(nw))
     assert rc == 0 and nw.value == 0 and meta[0] == 7 and meta[1] == 0
+
+
+# ------------------------------------------------------------------------------------ dense batches
+def unpack_dense(b, r):
+    """(tlen, flagged, codes[tlen], valid[tlen]) of read r of a kid.DenseBatch"""
+    a, e = int(b.boff[r]), int(b.boff[r + 1])
+    tlen = e - a
+    flagged = bool((int(b.flagbits[r >> 5]) >> (r & 31)) & 1)
+    pos = np.arange(a, e)
+    codes = ((b.codes[pos >> 4] >> (30 - 2 * (pos & 15)).astype(np.uint32)) & 3).astype(np.uint8)
+    valid = np.ones(tlen, np.uint8)
+    inv = b.inv[:b.n_inv]
+    mine = inv[(inv >= a) & (inv < e)]
+    valid[mine - a] = 0
+    return tlen, flagged, codes, valid
+
+
+@pytest.mark.parametrize("seed,n,kw,pieces", [
+    (41, 600, dict(), 1),
+    (42, 500, dict(ragged=True), 7),
+    (43, 400, dict(lower_rate=0.1, n_rate=0.02), 3),
+    (44, 300, dict(length=250, bad_tail=0.8), 5),
+    (45, 300, dict(length=31, bad_tail=0.5), 2),
+])
+def test_dense_packer_equals_word_packer(seed, n, kw, pieces):
+    """kid_pack_reads_dense (no padding, offsets only, non-ACGT bases as a position list) carries exactly
+    what kid_pack_reads does, read for read - also when a batch is appended to in several calls (base and
+    read positions that are not multiples of 16 / 32), and with every packer implementation."""
+    kid = _kid()
+    rng = np.random.default_rng(seed)
+    db = H.make_db(rng, 2000)
+    batch = H.make_reads(rng, db, n, **kw)
+    words, meta, span = kid.pack_reads(batch.seq, batch.qual, batch.off, want_span=True)
+    for impl in (0, kid.KID_PACK_IMPL_BYTES, kid.KID_PACK_IMPL_SWAR):
+        dense = kid.DenseBatch(batch.n, int(batch.off[-1]), flags=impl, max_inv=int(batch.off[-1]))
+        cuts = sorted(set([0, batch.n] + [int(x) for x in rng.integers(0, batch.n, size=pieces - 1)]))
+        spans = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            o = batch.off[a:b + 1] - batch.off[a]
+            lo, hi = int(batch.off[a]), int(batch.off[b])
+            spans.append(dense.append(batch.seq[lo:hi], batch.qual[lo:hi], o, want_span=True))
+        assert dense.n == batch.n and np.array_equal(np.concatenate(spans), span)
+        inv = dense.inv[:dense.n_inv]
+        assert np.all(np.diff(inv.astype(np.int64)) > 0)
+        for r in range(batch.n):
+            ht, hf, hc, hv, _, _ = unpack(words, meta, r)
+            dt, df, dc, dv = unpack_dense(dense, r)
+            assert (dt, df) == (ht, hf), r
+            assert np.array_equal(dc, hc) and np.array_equal(dv, hv), r
+        assert dense.n_bases == int(dense.boff[batch.n]) == sum(int(meta[2 * r + 1]) for r in range(batch.n))
+        # nothing but zeros behind the last base
+        tail = dense.codes[(dense.n_bases + 15) >> 4:((dense.n_bases + 15) >> 4) + 2]
+        assert not tail.any()
+        if dense.n_bases & 15:
+            assert (int(dense.codes[dense.n_bases >> 4]) & ((1 << (2 * (16 - (dense.n_bases & 15)))) - 1)) == 0
+
+
+def test_dense_packer_errors():
+    kid = _kid()
+    seq = np.frombuffer(b"ACGN" * 40, dtype=np.uint8)
+    qual = np.full(160, ord("I"), np.uint8)
+    off = np.array([0, 160], np.uint64)
+    small = kid.DenseBatch(4, 160, max_inv=3)
+    with pytest.raises(kid.KidError):  # 40 positions do not fit 3
+        small.append(seq, qual, off)
+    tiny = kid.DenseBatch(4, 160, codes=np.zeros(4, np.uint32))
+    with pytest.raises(kid.KidError):
+        tiny.append(seq, qual, off)
