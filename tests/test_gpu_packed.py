@@ -258,3 +258,56 @@ def test_dense_async_slots():
     for i in range(len(batches)):
         assert np.array_equal(outs[i], want[i]), i
     _check_counts(gs, osamp)
+
+
+def test_block_strip_and_window_boundaries():
+    """Read lengths on every internal boundary of the scan: a block is 128 k-mers (lengths 157-161,
+    285-289), the strip holds 2048 bases (2040-2080, flagged reads carry validity words so their limit is
+    lower: 1360-1372), a long read is walked in windows of 1920 k-mers (1948-1951, 3868-3871) - as text,
+    as packed and as dense batches, with and without non-ACGT bases."""
+    import kmer_id_b200 as kid
+    rng = np.random.default_rng(36)
+    db = H.make_db(rng, 20000)
+    odb, osamp = _oracle(db)
+    gdb, gs = _gpu(db)
+    lengths = (list(range(155, 163)) + list(range(283, 291)) + list(range(1358, 1374)) + list(range(2040, 2082)) +
+               [1947, 1948, 1949, 1950, 1951, 1952, 3867, 3868, 3869, 3870, 3871, 3872, 5789, 5790])
+    seqs, quals = [], []
+    keys_b = [H.key_to_bases(int(k)) for k in db.keys[:400]]
+    for L in lengths:
+        for with_n in (False, True):
+            parts, tot = [], 0
+            while tot < L:
+                p = keys_b[int(rng.integers(0, len(keys_b)))] if rng.random() < 0.5 else H._BASES[rng.integers(0, 4, size=17)]
+                parts.append(p)
+                tot += p.size
+            s = np.concatenate(parts)[:L].copy()
+            if with_n:
+                s[rng.integers(0, L, size=max(1, L // 300))] = ord("N")
+                s[L - 1] = ord("n") if rng.random() < 0.5 else s[L - 1]
+            seqs.append(s)
+            quals.append(np.full(L, ord("I"), np.uint8))
+    off = np.concatenate([[0], np.cumsum([s.size for s in seqs])]).astype(np.uint64)
+    seq, qual = np.concatenate(seqs), np.concatenate(quals)
+    n = len(seqs)
+    fin_o, _ = osamp.classify(seq, qual, off)
+    assert (fin_o > 1).sum() > n // 2
+    pad = np.zeros(16, np.uint8)
+    out_t = gs.classify(np.concatenate([seq, pad]), np.concatenate([qual, pad]), off)
+    assert np.array_equal(out_t, fin_o)
+    _check_counts(gs, osamp)
+    words, meta = kid.pack_reads(seq, qual, off)
+    out_p = np.full(n, -2, np.int32)
+    gs.classify_packed_host(words, meta, n, out_p)
+    osamp.classify(seq, qual, off)
+    assert np.array_equal(out_p, fin_o)
+    _check_counts(gs, osamp)
+    dense = kid.DenseBatch(n, int(off[-1]), max_inv=int(off[-1]))
+    dense.append(seq, qual, off)
+    for chunk in (1 << 18, 32):
+        gs.set_chunk_reads(chunk)
+        out_d = np.full(n, -2, np.int32)
+        gs.classify_dense_host(dense, out_d)
+        osamp.classify(seq, qual, off)
+        assert np.array_equal(out_d, fin_o)
+        _check_counts(gs, osamp)
