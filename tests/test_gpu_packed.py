@@ -291,7 +291,7 @@ def test_block_strip_and_window_boundaries():
     seq, qual = np.concatenate(seqs), np.concatenate(quals)
     n = len(seqs)
     fin_o, _ = osamp.classify(seq, qual, off)
-    assert (fin_o > 1).sum() > n // 2
+    assert (fin_o > 0).sum() > n // 2  # most reads hit something (mixed lineages fold to the root, taxon 1)
     pad = np.zeros(16, np.uint8)
     out_t = gs.classify(np.concatenate([seq, pad]), np.concatenate([qual, pad]), off)
     assert np.array_equal(out_t, fin_o)
