@@ -3,9 +3,9 @@
 //
 // Replaces, for a whole batch of reads, process_read (newkmer_10nx.cpp:452-617), Hashtable::getHash
 // (:204-233) and Tree1::msca (:118-144).  process_qual's trim (:714-760) and the ACGT test (:480-524)
-// happened when the batch was packed (kid_pack.cu on the device, kid_pack_reads on a host parser), so a
-// read arrives as `tlen` 2-bit codes that start on a word boundary, plus validity words only if it
-// contains a base outside ACGTacgt.
+// happened when the batch was packed (kid_pack_kernel from text, kid_expand_kernel from the dense batch
+// a host parser ships, or kid_pack_reads on the host), so a read arrives as `tlen` 2-bit codes that
+// start on a word boundary, plus validity words only if it contains a base outside ACGTacgt.
 //
 // Persistent grid, one 1024-thread block per SM; a warp takes kGroup consecutive reads at a time and
 // lane j of chunk c owns the k-mer that starts at base 32c+j of the current read.
@@ -18,9 +18,11 @@
 //           (128 k-mers, a whole 150-base read): the 16-mer hashes of 5 chunk positions are computed
 //           once (the fifth is the 14-lane halo of the fourth).
 //   MINIM   sliding minimum of the 16-mer hashes over 15 positions: 4 shuffle rounds (1,2,4,7).
-//   LOOKUP  sector = group(M) | sector(key); two chunks (64 k-mers) request their 32-byte sectors
-//           before the first is consumed, then the other two.  Lanes that share a minimizer share a
-//           128-byte line, so a warp-wide load touches ~5 lines instead of 32.
+//   LOOKUP  sector = group(M) | sector(key); all four chunks (128 k-mers) request the 16-byte first
+//           half of their sector (the high words of its three keys) before the first is consumed;
+//           only a lane whose high word matches reads the second half, from L1 (kid_table2.cuh).
+//           Lanes that share a minimizer share a 128-byte line, so a warp-wide load touches ~5 lines
+//           instead of 32.
 //   FOLD    hits are rare; a ballot finds them and the warp folds them strictly in position order
 //           with kid_msca (the fold is order dependent).
 //   COUNT   seen bit (atomicOr on the per-sample bitmap) for hits with taxon > 1 (:596-603),
