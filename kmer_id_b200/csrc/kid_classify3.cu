@@ -429,7 +429,7 @@ cudaError_t launch_hist(const KidPackedParams &p, int sm_count, cudaStream_t str
     return hist ? launch_one<true, F, MM, G, V>(p, sm_count, stream) : launch_one<false, F, MM, G, V>(p, sm_count, stream);
 }
 
-// measured (tools/gpu_i.sh, 20 M reads): per-chunk votes + range masks 15.69 ms; one vote per block 16.27;
+// measured (tools/gpu_runs/gpu_i.sh, 20 M reads): per-chunk votes + range masks 15.69 ms; one vote per block 16.27;
 // lane compare instead of range masks 15.53; both 15.94; first halves bypassing L1 (bit 2): 16.22
 constexpr int kVarDefault = 2;
 template <int F, int G = kGroupDefault, int V = kVarDefault>

@@ -82,7 +82,7 @@ __host__ __device__ __forceinline__ uint32_t kid_mm_hash_canon(uint32_t x)
 {
     // One multiply: the order is decided by the high bits of the product, which depend on every bit of
     // x.  The xor keeps x = 0 (poly-A / poly-T) from being the smallest value of all, i.e. from winning
-    // every window it occurs in.  Measured against multiply - xorshift - multiply (tools/gpu_m.sh):
+    // every window it occurs in.  Measured against multiply - xorshift - multiply (tools/gpu_runs/gpu_m.sh):
     // fewer displaced keys (83 k vs 98 k at bact10 scale, 19.5 M vs 24.9 M at 10x) and 1-4 % more lookups/s.
     return (x ^ 0x5BD1E995u) * 0x9E3779B1u;
 }
