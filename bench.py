@@ -676,11 +676,16 @@ def run_reference(args):
     timed = steps[args.warmup:] if len(steps) > args.warmup else steps
     sec = statistics.mean(s for s, _ in timed)
     value = pairs / sec
-    cfg = workload_config(args, n_probes, den=den, pairs=pairs)
+    # the arm's own config (the contract: "on your arm's config ... each step a bounded sample of that
+    # workload"); what was actually run per step is spelled out in `sample` and cpu_baseline.sample.  A
+    # probe DB that is NOT the benchmark's (den != 1) changes the workload and therefore the config.
+    cfg = workload_config(args, n_probes, den=den)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
            "config": cfg,
+           "sample": {"pairs_per_step": pairs, "db_probes": n_probes, "db_den": den, "steps_in_one_process": n_samples,
+                      "db_load_s": load_s, "input_generation_s": t_gen},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                             "sample": "unmodified nk10 (g++ -O3), 1 thread (it has no threading); probe DB = refkey counts / %d "
                                       "(%d lines of text)%s in its 2^30-cell table, %d pairs per step (the GPU arm: %d), "
@@ -717,7 +722,8 @@ def run_reference_port(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / int32 counts", "data": "synthetic",
-           "config": workload_config(args, wl.n_probes, den=den, pairs=pairs),
+           "config": workload_config(args, wl.n_probes, den=den),
+           "sample": {"pairs_per_step": pairs, "db_probes": int(keys.size), "db_den": den},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": "oracle/kid_oracle.c, probe DB = refkey counts x %d / %d (%d keys), %d pairs per step (the GPU arm: %d)"
                                       % (args.cfg["num"], den, keys.size, pairs, args.pairs)},
