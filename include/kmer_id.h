@@ -118,7 +118,9 @@ int kid_sample_begin(kid_sample *s, void *stream); /* zero gcount/seen/counters,
  *   out_taxon   device int32[n_reads] or NULL: final_targ (:616), or -1 if the read was dropped
  *               by the length rule (:755) and therefore not counted anywhere.
  *   out_span    device uint32[2*n_reads] or NULL: trimmed (start, stop) (:724-753)
- * Accumulates gcount, seen flags and the lookup/hit counters into s.  Asynchronous. */
+ * Accumulates gcount, seen flags and the lookup/hit counters into s.  The work (kid_pack_kernel, then
+ * the scan) is asynchronous on `stream`; the call itself waits once for the stream to hand back
+ * off[n_reads], which sizes the packed scratch buffer. */
 int kid_classify_device(kid_sample *s, const uint8_t *seq, const uint8_t *qual,
                         const uint64_t *off, size_t n_reads, int32_t *out_taxon,
                         uint32_t *out_span, void *stream);
@@ -196,6 +198,7 @@ int kid_classify_packed_host(kid_sample *s, const uint32_t *words, uint32_t word
  *             codes[0] holds bases 16*(base0/16) .. of the stream (base0 = what kid_pack_reads_dense got).
  *   boff      uint32[n_reads+1]
  *   flagbits  bit (read0 + r) % 32 of word (read0 + r) / 32: read r contains a base outside ACGT
+ *             (kid_pack_reads_dense zeroes a word when it packs the word's first read)
  *   inv       uint32[n_inv]: stream positions of those bases, ascending
  * kid_pack_reads_dense appends n_reads reads to a batch (base0 / read0 = bases / reads already in it; the
  * arrays it is given start at the batch's beginning for flagbits, at the append position for the
