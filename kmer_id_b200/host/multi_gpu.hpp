@@ -61,6 +61,7 @@ public:
         samples.assign(n, nullptr);
         for (size_t i = 0; i < n; i++)
             if (kid_sample_create(dbs[i], &samples[i]) != 0) { msg = kid_last_error(); return false; }
+        warm();
         if (n > 1) {
             if (kid_peer_enable(devices.data(), (int)n) != 0) { msg = kid_last_error(); return false; }
 #ifdef KID_HAVE_NCCL
@@ -82,6 +83,27 @@ public:
     }
 
     bool uses_nccl() const { return nccl_; }
+
+    // One tiny dense batch through every slot of every shard: loads the kernels (CUDA loads a module on its
+    // first launch), creates the slot streams and their first buffers, so that the first sample does not pay
+    // for it.  The accumulators it touches are cleared by the kid_sample_begin that starts every sample.
+    void warm()
+    {
+        static const char bases[] = "ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"; // 64
+        void *pin = nullptr;
+        if (kid_host_alloc(&pin, 4096) != 0) return;
+        uint32_t *codes = (uint32_t *)pin, *boff = codes + 64, *flagbits = codes + 80, *inv = codes + 96;
+        int32_t *taxon = (int32_t *)(codes + 128);
+        const uint64_t off[2] = { 0, 64 };
+        size_t ni = 0;
+        uint32_t nb = 0;
+        if (kid_pack_reads_dense((const uint8_t *)bases, nullptr, off, 1, 0, 0, codes, 64, boff, flagbits, 0, inv, 16, &ni, nullptr, &nb) == 0)
+            for (kid_sample *s : samples) {
+                for (int slot = 0; slot < KID_MAX_SLOTS; slot++) kid_classify_dense_async(s, slot, codes, boff, flagbits, inv, ni, 1, taxon);
+                for (int slot = 0; slot < KID_MAX_SLOTS; slot++) kid_wait(s, slot);
+            }
+        kid_host_free(pin);
+    }
 
     bool begin(std::string &msg)
     {
