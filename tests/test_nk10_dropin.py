@@ -134,3 +134,33 @@ def test_probe_cache_round_trip(tmp_path):
     assert b"3100 kmers loaded" in r3.stdout
     ref = H.run_nk10(NK_REF, work, fq)
     assert ref.stdout == r3.stdout
+
+
+@pytest.mark.skipif(NK_REF is None, reason="oracle/_ref/nk10_small not built")
+def test_quality_line_shorter_than_its_read_aborts_like_the_reference(tmp_path):
+    """qual.at(stop) throws std::out_of_range in the reference (newkmer_10nx.cpp:729) and nothing catches
+    it: SIGABRT.  The drop-in dies the same way (from a parse worker or from the reader thread) instead
+    of classifying a record the reference never would."""
+    rng = np.random.default_rng(3005)
+    db = H.make_db(rng, 2000)
+    work = str(tmp_path)
+    fq = os.path.join(work, "fq")
+    os.makedirs(fq)
+    H.make_bact10_dir(work, db)
+    a = H.make_reads(rng, db, 300)
+    H.write_fastq_gz(os.path.join(fq, "q_R2_tr.fastq.gz"), a)
+    import gzip
+    recs = []
+    for r in range(a.n):
+        lo, hi = int(a.off[r]), int(a.off[r + 1])
+        q = a.qual[lo:hi].tobytes()
+        if r == 200:
+            q = q[:-7]
+        recs.append(a.names[r] + b"\n" + a.seq[lo:hi].tobytes() + b"\n+\n" + q + b"\n")
+    with gzip.open(os.path.join(fq, "q_R1_tr.fastq.gz"), "wb") as f:
+        f.write(b"".join(recs))
+    r_ref = H.run_nk10(NK_REF, work, fq)
+    assert r_ref.returncode == -6 and b"out_of_range" in r_ref.stderr
+    for env in ({}, {"KID_PARSE_THREADS": "0"}, {"KID_SERIAL": "1"}):
+        r_gpu = subprocess.run([NK_GPU, fq + "/"], cwd=work, capture_output=True, timeout=300, env=dict(os.environ, **env))
+        assert r_gpu.returncode == -6 and b"out_of_range" in r_gpu.stderr, (env, r_gpu.returncode, r_gpu.stderr[-300:])
