@@ -251,11 +251,12 @@ int kid_db_build(const uint64_t *keys, const uint32_t *taxa, size_t n_keys, int 
 
     // Beyond 4e8 keys the m = 16 minimizers saturate (kid_table2.cuh): a minimizer then addresses 2 or 4
     // lines instead of one (KID_DB_SUB_BITS=2|3|4 overrides).  KID_DB_MM=20 selects 20-mer minimizers
-    // instead (one line per minimizer again).  Measured at 1.09e9 keys in 2^31 sectors: m = 16 with two
-    // lines per minimizer 24.9 M keys displaced, 107 G lookups/s; m = 20: 31.0 M displaced, 101 G - its
-    // 32-bit ordering hash saturates the same way (the minimum of 11 hashes lies in the lowest twelfth of
-    // the range, so 1e9 winners share ~4e8 values); it would take a second word of identity carried
-    // through the sliding minimum to address lines by.  Hence m = 16 stays the default at every size.
+    // instead (one line per minimizer again; each candidate carries an (order, identity) pair through
+    // the sliding minimum, kid_table2.cuh).  Measured at 1.09e9 keys in 2^31 sectors
+    // (tools/gpu_runs/gpu_t.sh): m = 16 with two lines per minimizer 19.5 M keys displaced (1.8 %), 110 G
+    // lookups/s; m = 20: 4.6 M displaced (0.42 %) but 101 G lookups/s - the 64-bit sliding minimum and the
+    // shorter runs (11 windows instead of 15: more DRAM lines per warp) cost more than the second probes
+    // they save.  Hence m = 16 stays the default at every size.
     int sub_bits = 2, mm = 16;
     if (layout == KID_LAYOUT_MINIMIZER) {
         if (const char *e = getenv("KID_DB_MM")) {

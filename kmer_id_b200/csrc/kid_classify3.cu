@@ -30,6 +30,7 @@
 #include "kid_kernels.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -196,7 +197,9 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
     uint32_t W[kW];
 #pragma unroll
     for (int i = 0; i < kW; i++) W[i] = cw[i];
-    uint32_t cm[5]; // minimizer-candidate hashes -> sliding minima
+    // minimizer candidates -> sliding minima: the 32-bit hash of a 16-mer, or the (order, identity) pair of a 20-mer
+    using MinT = typename std::conditional<kMM == 16, uint32_t, uint64_t>::type;
+    MinT cm[5];
     uint64_t key[4];
 #pragma unroll
     for (int u = 0; u < 5; u++) {
@@ -208,14 +211,14 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
             rl = kid_rc16(lo);
         }
         if (kMM == 16) {
-            cm[u] = kid_mm_hash_canon(min(hi, rc));
+            cm[u] = (MinT)kid_mm_hash_canon(min(hi, rc));
         } else {
             // canonical 20-mer as (top 32 bits, low 8 bits): forward = bases 0..19, reverse complement =
             // that of bases 16..19 in front of that of bases 0..15 (kid_table2.cuh)
             const uint32_t ft = hi, fl = lo >> 24;
             const uint32_t rt = ((rl & 0xFFu) << 24) | (rc >> 8), rlo = rc & 0xFFu;
             const bool fwd = ft < rt || (ft == rt && fl < rlo);
-            cm[u] = kid_mm20_hash_canon(fwd ? ft : rt, fwd ? fl : rlo);
+            cm[u] = (MinT)kid_mm20_pair(fwd ? ft : rt, fwd ? fl : rlo);
         }
         if (u < 4) {
             // forward key = first 30 of the 32 bases at this position; the reverse complement of 32
@@ -232,12 +235,12 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
         const int d = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : (kMM == 16 ? 7 : 3);
         const int src = lane + d; // shfl takes the source lane modulo 32
         const bool wrap = lane + d >= 32;
-        uint32_t s[5];
+        MinT s[5];
 #pragma unroll
         for (int u = 0; u < 5; u++) s[u] = __shfl_sync(full, cm[u], src);
 #pragma unroll
         for (int u = 0; u < 4; u++) cm[u] = min(cm[u], wrap ? s[u + 1] : s[u]);
-        if (step < 3) cm[4] = min(cm[4], wrap ? 0xFFFFFFFFu : s[4]);
+        if (step < 3) cm[4] = min(cm[4], wrap ? (MinT)~(MinT)0 : s[4]);
     }
     // which of the 128 positions are k-mer starts: inside the read (the first nvb positions of the
     // block) and, for a read with non-ACGT bases, the start of a run of 30 valid bases (kmask: position
@@ -261,7 +264,7 @@ __device__ __forceinline__ void scan_block(const KidPackedParams &p, const Kid2T
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-        const uint32_t grp = (cm[u] * 0x9E3779B1u) >> tab.line_shift;
+        const uint32_t grp = ((uint32_t)cm[u] * 0x9E3779B1u) >> tab.line_shift; // (m = 20: the winner's identity word)
         sec[u] = (grp << tab.sub_bits) | (kid_key_hash32(key[u]) >> (32 - tab.sub_bits));
     }
     // every sector index is known before the first load goes out, so that the compiler cannot slide

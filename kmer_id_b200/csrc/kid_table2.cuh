@@ -103,33 +103,36 @@ __host__ __device__ __forceinline__ uint32_t kid_minimizer(uint64_t key)
     return m;
 }
 
-// ---- m = 20 for very large databases ------------------------------------------------------------
+// ---- m = 20 for very large databases (KID_DB_MM=20) ------------------------------------------------
 // Only ~10 % of the 2^31 canonical 16-mers ever win a 15-way minimum, so beyond a few 1e8 keys several
 // keys share every minimizer and pile into its 12-entry line.  A 20-mer minimizer (11 windows, 2^39
-// canonical values) gives practically every key of a 1e9-key database its own.  The canonical 20-mer
-// is kept as (top 32 bits, low 8 bits); only the order of the hash matters.
+// canonical values) gives practically every key of a 1e9-key database its own - but a 32-bit word cannot
+// say which: the minimum of 11 hashes lies in the lowest twelfth of the range, so 1e9 winners share
+// ~4e8 values whatever the hash.  Each candidate therefore carries 64 bits, (order hash, identity hash),
+// the sliding minimum runs over the pair, and the winner's IDENTITY word addresses the line.
+// The canonical 20-mer is handled as (top 32 bits, low 8 bits).
 #define KID_MM20 20
 #define KID_MM20_WINDOWS (30 - KID_MM20 + 1) /* 11 */
-__host__ __device__ __forceinline__ uint32_t kid_mm20_hash_canon(uint32_t top, uint32_t low8)
+__host__ __device__ __forceinline__ uint64_t kid_mm20_pair(uint32_t top, uint32_t low8)
 {
-    uint32_t x = top * 0x9E3779B1u ^ low8 * 0xC2B2AE3Du;
-    x ^= x >> 15;
-    x *= 0x85EBCA77u;
-    return x;
+    const uint32_t order = (top ^ 0x5BD1E995u) * 0x9E3779B1u ^ low8 * 0xC2B2AE3Du;
+    const uint32_t ident = (top ^ 0x7F4A7C15u) * 0x85EBCA77u + low8 * 0x27D4EB2Fu;
+    return ((uint64_t)order << 32) | ident;
 }
-// minimizer hash of a 60-bit key with 20-mer candidates (build side)
+// what addresses the line of a 60-bit key with 20-mer minimizers (build side): the identity word of the
+// smallest (order, identity) pair among its 11 candidates
 __host__ __device__ __forceinline__ uint32_t kid_minimizer20(uint64_t key)
 {
-    uint32_t m = 0xFFFFFFFFu;
+    uint64_t m = ~0ull;
     for (int i = 0; i < KID_MM20_WINDOWS; i++) {
         const uint64_t f = (key >> (2 * (KID_MM20_WINDOWS - 1 - i))) & ((1ULL << 40) - 1ULL); // bases i..i+19
         // reverse complement of 20 bases: that of the 16 first bases below that of the last 4
         const uint64_t r = ((uint64_t)(kid_rc16((uint32_t)(f << 24)) & 0xFFu) << 32) | kid_rc16((uint32_t)(f >> 8));
         const uint64_t c = f < r ? f : r;
-        const uint32_t h = kid_mm20_hash_canon((uint32_t)(c >> 8), (uint32_t)(c & 0xFFu));
+        const uint64_t h = kid_mm20_pair((uint32_t)(c >> 8), (uint32_t)(c & 0xFFu));
         m = h < m ? h : m;
     }
-    return m;
+    return (uint32_t)m;
 }
 __host__ __device__ __forceinline__ uint32_t kid_minimizer_mm(uint64_t key, int mm)
 {
