@@ -287,3 +287,50 @@ def test_reader_packed_batches_match_text_batches_and_oracle_trim(tmp_path):
     assert r0[0][5] == b"ACGN" * 20 and r1[0][5] == b"ACGT" * 20 and r0[1][5] == b"ACGTNNACGT" + b"ACGT" * 10
     assert (int(r0[0][4]), int(r1[0][4]), int(r0[1][4])) == (1, 0, 1)
     assert r0[2][0] == b"big" and r0[2][5] == big and int(r0[2][3]) == 30000 and r0[3][5] == b"ACGT" * 10
+
+
+def test_reader_fuzz_parallel_framing_against_serial_text_reader(tmp_path):
+    """Random FASTQ files full of the reference's parser quirks (CRLF, blank and "\\r"-only lines anywhere,
+    '+' lines with text, long quality lines, unterminated last record, several gzip members, 0 to 600
+    records of 1 to 1000 bases) through the hosts' reader with 0, 1 and 3 framing threads and 4 KiB
+    super-blocks: record for record what the serial text reader + the oracle's trim give."""
+    import random
+    rnd = random.Random(20261018)
+    lut = np.full(256, ord("N"), np.uint8)
+    for ch in b"ACGT":
+        lut[ch] = ch
+        lut[ch | 0x20] = ch
+    p = os.path.join(str(tmp_path), "fz.fastq.gz")
+    for it in range(36):
+        n = rnd.choice([0, 1, 2, 3, 5, 17, 60, 200, 600])
+        fq = b""
+        for r in range(n):
+            L = rnd.choice([1, 2, 29, 30, 31, 32, 50, 100, 150, 151, 300, 1000])
+            s = bytes(rnd.choice(b"ACGTACGTACGTNacgtn") for _ in range(L))
+            q = bytes(rnd.choice(b"#+05?I!~") for _ in range(L + rnd.choice([0, 0, 0, 3])))
+            eol = rnd.choice([b"\n", b"\r\n"])
+            blank = lambda: rnd.choice([b"", b"", b"", b"\n", b"\r\n", b"\n\n"])
+            fq += b"@r%d x" % r + eol + blank() + s + eol + blank() + rnd.choice([b"+", b"+r%d" % r]) + eol + blank() + q + eol + blank()
+        if rnd.random() < 0.3:
+            fq += b"@tail\nACGTACGTACGTACGTACGTACGTACGTACGTAC"  # unterminated: dropped
+        members = rnd.choice([1, 1, 3])
+        with open(p, "wb") as f:
+            step = max(1, (len(fq) + members - 1) // members)
+            for i in range(0, max(len(fq), 1), step):
+                f.write(gzip.compress(fq[i:i + step], 1))
+        text = _records("gzfastq", p)
+        for th in ("0", "1", "3"):
+            env = dict(os.environ, KID_PARSE_THREADS=th, KID_GZ_MIN_BYTES="0",
+                       KID_GZ_PIECE_BYTES=str(rnd.choice([2048, 8192, 1 << 20])))
+            r = subprocess.run([DUMP, "packed", "gzfastq", p, "0"], capture_output=True, timeout=120, env=env)
+            assert r.returncode == 0, r.stderr
+            rows = [l.split(b"\t") for l in r.stdout.split(b"\n") if l]
+            assert len(rows) == len(text), (it, th)
+            for (acc, seq, qual), row in zip(text, rows):
+                st, sp = kor.trim(qual, len(seq))
+                assert row[0] == acc and (int(row[1]), int(row[2])) == (st, sp), (it, th, acc)
+                if sp - st < 30:
+                    assert int(row[3]) == 0
+                    continue
+                want = lut[np.frombuffer(seq[st:sp + 1], np.uint8)].tobytes()
+                assert int(row[3]) == sp - st + 1 and row[5] == want and int(row[4]) == int(b"N" in want), (it, th, acc)
