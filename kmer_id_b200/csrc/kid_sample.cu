@@ -5,14 +5,26 @@
 // the per-slot seen bits - no k-mer set is needed.
 #include "kid_kernels.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
+#define KID_UCOUNT_THREADS 1024
+
 namespace {
 
 // N_SRC == 0: one local bitmap (src.p[0]); otherwise OR of n_src bitmaps, possibly peer memory
-template <int LAYOUT, bool MULTI>
-__global__ void __launch_bounds__(256)
+// SMEM: the block counts into a shared-memory histogram (n_taxa ints) and adds its non-zero rows to
+// ucount once at the end - a sample's hits pile onto few taxa, and global atomics on one address queue up
+template <int LAYOUT, bool MULTI, bool SMEM>
+__global__ void __launch_bounds__(KID_UCOUNT_THREADS)
 kid_ucount_kernel(const void *__restrict__ slots_, const KidPtrList src, int n_src,
                   uint64_t quad0, uint64_t n_quads, int *ucount, int n_taxa)
 {
+    extern __shared__ int uhist[];
+    if (SMEM) {
+        for (int i = threadIdx.x; i < n_taxa; i += blockDim.x) uhist[i] = 0;
+        __syncthreads();
+    }
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
          q += (uint64_t)gridDim.x * blockDim.x) {
         uint4 v;
@@ -42,8 +54,15 @@ kid_ucount_kernel(const void *__restrict__ slots_, const KidPtrList src, int n_s
                     const uint32_t *w = static_cast<const uint32_t *>(slots_) + 8 * sec;
                     taxon = kid2_taxon_of(__ldg(w + 3), __ldg(w + 7), (int)(slot - sec * KID2_SLOTS_PER_SECTOR));
                 }
-                if (taxon < (uint32_t)n_taxa) atomicAdd(ucount + taxon, 1);
+                if (taxon < (uint32_t)n_taxa) atomicAdd((SMEM ? uhist : ucount) + taxon, 1);
             }
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_taxa; i += blockDim.x) {
+            const int c = uhist[i];
+            if (c) atomicAdd(ucount + i, c);
         }
     }
 }
@@ -97,6 +116,30 @@ unsigned grid_for(uint64_t n, unsigned threads)
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+
+template <int LAYOUT, bool MULTI>
+cudaError_t launch_ucount(const void *slots, const KidPtrList &src, int n_src, uint64_t word0, uint64_t n_words,
+                          int *ucount, int n_taxa, cudaStream_t stream)
+{
+    static const bool want_smem = getenv("KID_UCOUNT_GLOBAL") == nullptr;
+    const size_t smem = (size_t)n_taxa * sizeof(int);
+    if (want_smem && smem <= KID_SMEM_HIST_MAX_BYTES) {
+        auto kern = kid_ucount_kernel<LAYOUT, MULTI, true>;
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        // few, large blocks: every block flushes its histogram once
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(148ull * 2, (n_words / 4 + KID_UCOUNT_THREADS - 1) / KID_UCOUNT_THREADS));
+        kern<<<blocks, KID_UCOUNT_THREADS, smem, stream>>>(slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
+    } else {
+        kid_ucount_kernel<LAYOUT, MULTI, false><<<grid_for(n_words / 4, KID_UCOUNT_THREADS), KID_UCOUNT_THREADS, 0, stream>>>(
+            slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
+    }
+    KID_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 } // namespace
 
 cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *seen, uint64_t word0,
@@ -105,28 +148,16 @@ cudaError_t kid_launch_ucount(const void *slots, int layout, const uint32_t *see
     if (n_words == 0) return cudaSuccess;
     KidPtrList l;
     for (int i = 0; i < KID_MAX_OR_SOURCES; i++) l.p[i] = i == 0 ? seen : nullptr;
-    if (layout == KID_LAYOUT_KEYHASH)
-        kid_ucount_kernel<KID_LAYOUT_KEYHASH, false><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, l, 1, word0 / 4, n_words / 4, ucount, n_taxa);
-    else
-        kid_ucount_kernel<KID_LAYOUT_MINIMIZER, false><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, l, 1, word0 / 4, n_words / 4, ucount, n_taxa);
-    KID_COUNT_LAUNCH();
-    return cudaGetLastError();
+    return layout == KID_LAYOUT_KEYHASH ? launch_ucount<KID_LAYOUT_KEYHASH, false>(slots, l, 1, word0, n_words, ucount, n_taxa, stream)
+                                        : launch_ucount<KID_LAYOUT_MINIMIZER, false>(slots, l, 1, word0, n_words, ucount, n_taxa, stream);
 }
 
 cudaError_t kid_launch_ucount_or(const void *slots, int layout, const KidPtrList &src, int n_src, uint64_t word0,
                                  uint64_t n_words, int *ucount, int n_taxa, cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
-    if (layout == KID_LAYOUT_KEYHASH)
-        kid_ucount_kernel<KID_LAYOUT_KEYHASH, true><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
-    else
-        kid_ucount_kernel<KID_LAYOUT_MINIMIZER, true><<<grid_for(n_words / 4, 256), 256, 0, stream>>>(
-            slots, src, n_src, word0 / 4, n_words / 4, ucount, n_taxa);
-    KID_COUNT_LAUNCH();
-    return cudaGetLastError();
+    return layout == KID_LAYOUT_KEYHASH ? launch_ucount<KID_LAYOUT_KEYHASH, true>(slots, src, n_src, word0, n_words, ucount, n_taxa, stream)
+                                        : launch_ucount<KID_LAYOUT_MINIMIZER, true>(slots, src, n_src, word0, n_words, ucount, n_taxa, stream);
 }
 
 cudaError_t kid_launch_seen_or(uint32_t *dst, const KidPtrList &src, int n_src, uint64_t word0,
