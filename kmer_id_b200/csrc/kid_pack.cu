@@ -8,8 +8,9 @@
 //
 // A warp takes 32 consecutive reads at a time.
 //   TRIM  one lane per read: a read whose first and last quality byte and 4-base window pass (nearly
-//         all good reads) is decided from 8 bytes; the others go through the warp-cooperative search
-//         of kid_readprep.cuh one after the other.
+//         all good reads) is decided from 8 bytes; a short bad head or tail is walked by the lane itself
+//         (process_qual's loops as they stand, up to 96 steps); only longer runs go through the
+//         warp-cooperative searches of kid_readprep.cuh, one read after the other.
 //   PACK  one lane per 32 bases of trimmed sequence, over all 32 reads (a prefix sum of the reads'
 //         unit counts in shared memory, a 5-step binary search per unit): nine aligned 32-bit loads,
 //         byte realignment with funnel shifts, SIMD-in-word packing (kid_readprep.cuh) -> two code
@@ -84,6 +85,9 @@ kid_pack_kernel(const KidPackParams p)
                 // both end bases and both end windows pass: nothing to trim
                 slow = !(a0 >= 49 && b0 >= 49 && a0 + a1 + a2 + a3 - 128 >= 68 && b0 + b1 + b2 + b3 - 128 >= 68);
             }
+            // a short bad head or tail: the lane walks it itself, all such lanes of the warp at once; only a
+            // long run of bad qualities goes on to the warp-cooperative searches
+            if (slow) slow = !trim_read_lane(q, len, 96, start, stop);
             unsigned todo = __ballot_sync(full, slow);
             while (todo) { // the warp-cooperative search, one read after the other
                 const int i = __ffs(todo) - 1;

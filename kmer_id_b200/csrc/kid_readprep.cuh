@@ -122,3 +122,38 @@ __device__ __forceinline__ void trim_read(const signed char *q, int len, int qa,
     }
 }
 
+// ---- TRIM, one lane per read: process_qual's four loops (:727-753) as they stand, for the ordinary case
+// of a short low-quality head or tail.  Returns false when `budget` steps were not enough (a long run of
+// bad qualities): the caller then hands the read to the warp-cooperative searches above.
+__device__ __forceinline__ bool trim_read_lane(const signed char *q, int len, int budget, int &start, int &stop)
+{
+    start = 0;
+    stop = len - 1;
+    if (len <= 0) return true;
+    while (start < stop && q[start] < 49) { // :727-728
+        start++;
+        if (--budget < 0) return false;
+    }
+    while (stop > start && q[stop] < 49) { // :729-730
+        stop--;
+        if (--budget < 0) return false;
+    }
+    if (start < stop - 4) { // :732-742 leading 4-base window
+        int w = q[start] + q[start + 1] + q[start + 2] + q[start + 3] - 128;
+        while (w < 68 && start < stop - 4) {
+            w += q[start + 4] - q[start];
+            start++;
+            if (--budget < 0) return false;
+        }
+    }
+    if (start < stop - 4) { // :743-753 trailing window
+        int w = q[stop] + q[stop - 1] + q[stop - 2] + q[stop - 3] - 128;
+        while (w < 68 && start < stop - 4) {
+            w += q[stop - 4] - q[stop];
+            stop--;
+            if (--budget < 0) return false;
+        }
+    }
+    return true;
+}
+
