@@ -12,13 +12,13 @@ CUDA_HOME ?= /usr/local/cuda
 
 CSRC := kmer_id_b200/csrc
 LIB  := kmer_id_b200/libkmerid_b200.so
-LIB_OBJS := $(CSRC)/kid_api.o $(CSRC)/kid_classify.o $(CSRC)/kid_classify3.o $(CSRC)/kid_pack.o $(CSRC)/kid_pack_host.o $(CSRC)/kid_build_sorted.o $(CSRC)/kid_sample.o
+LIB_OBJS := $(CSRC)/kid_api.o $(CSRC)/kid_classify.o $(CSRC)/kid_classify3.o $(CSRC)/kid_pack.o $(CSRC)/kid_pack_host.o $(CSRC)/kid_build_sorted.o $(CSRC)/kid_sample.o $(CSRC)/kid_ingest.o
 
 all: lib tools host oracle
 
 lib: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kid_common.cuh $(CSRC)/kid_table2.cuh $(CSRC)/kid_kernels.cuh $(CSRC)/kid_readprep.cuh include/kmer_id.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kid_common.cuh $(CSRC)/kid_table2.cuh $(CSRC)/kid_kernels.cuh $(CSRC)/kid_readprep.cuh $(CSRC)/kid_internal.cuh $(CSRC)/kid_inflate.cuh $(CSRC)/kid_inflate_chain.hpp include/kmer_id.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(CSRC)/%.o: $(CSRC)/%.cpp include/kmer_id.h

@@ -36,6 +36,7 @@ extern "C" {
 #define KID_ERANGE (-4)  /* taxon id or tree node outside [0, n_taxa) (UB in the reference) */
 #define KID_ETREE (-5)   /* taxonomy has a cycle that never reaches the root (reference hangs) */
 #define KID_EFULL (-6)   /* table could not place every key (reference: "out of memory in table") */
+#define KID_EUNSUPPORTED (-7) /* kid_fastq_load_gz_file: a file for the host reader; nothing was counted */
 
 /* flags for kid_db_build */
 #define KID_DB_ACCEPT_U 1u /* reads: U/u count as T (kmer_read_vf6.cpp:496-500,521-525) */
@@ -106,6 +107,7 @@ int kid_db_table_device(const kid_db *db, void **table, uint64_t *n_sectors);
 int kid_sample_create(const kid_db *db, kid_sample **out);
 void kid_sample_free(kid_sample *s);
 int kid_sample_begin(kid_sample *s, void *stream); /* zero gcount/seen/counters, asynchronously */
+const kid_db *kid_sample_db(const kid_sample *s);   /* the database the sample was created for */
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * kid_classify_device: replaces process_qual (:714-760) + process_read (:452-617) +
@@ -289,6 +291,44 @@ int kid_sample_use_seen_buffer(kid_sample *s, uint32_t *buf, uint64_t n_words);
  * histograms are additive, so a sum-all-reduce finishes the job. */
 int kid_ucount_range_device(const kid_db *db, const uint32_t *seen, uint64_t word0,
                             uint64_t n_words, int32_t *ucount_partial, void *stream);
+
+/* ---- gzip FASTQ files read on the device -----------------------------------------------------------
+ * Replaces process_fqgz (newkmer_10nx.cpp:762-816: gzread, line splitting, the 4-line state) together
+ * with process_qual/process_read for a WHOLE file: the compressed bytes are copied to the device and
+ * inflated there (csrc/kid_inflate.cuh: speculative inflate of 32 KiB pieces to 16-bit symbols, chained
+ * and CRC-checked), lines are framed with two prefix sums (newlines; non-empty lines, whose count mod 4
+ * is the reference's mod4), and the records go through kid_pack_kernel and the k-mer scan.  The host
+ * only sees per-read taxa and, on request, the header and trimmed bases of chosen reads.
+ *   kid_fastq_load_gz_file  KID_OK: the file is on the device, framed; *n_reads = its records.
+ *                           KID_EUNSUPPORTED: a file this path does not reproduce byte for byte (no gzip
+ *                           header, fixed/stored-only deflate streams, trailing bytes or a bad CRC-32 /
+ *                           ISIZE - zlib has to judge those -, a line of >= 16 KiB (fatal at :773), a
+ *                           quality line shorter than its read (the reference aborts at :729), more than
+ *                           4 GiB of text or than device memory holds).  Nothing has been counted: read
+ *                           the file with the host reader, whose error behaviour is the reference's.
+ *   kid_fastq_prefetch_gz_file  optional: starts reading `path` into a second device buffer on a helper thread
+ *                           and returns at once; a later kid_fastq_load_gz_file of the same path finds the
+ *                           bytes there (the host reads sample i+1 while the device works on sample i).
+ *   kid_fastq_classify      all records of the loaded file into sample s (same device); out_taxon: host
+ *                           int32[n_reads] (page-locked for speed) or NULL, -1 = dropped by the length rule.
+ *   kid_fastq_fetch         for n record indices: *lens = uint32[2n] (header length, trimmed bases
+ *                           length), *data = header_0 bases_0 header_1 bases_1 ... (no separators; the
+ *                           header is the whole '@' line without its line end, what :796 keeps as acc);
+ *                           both live in the object until its next call.  For _reads.txt (:608-611).
+ *   kid_fastq_stats         text bytes, pieces, pieces inflated twice, gzip members, and the seconds of the
+ *                           last file's phases: read+copy, find, inflate, chain, resolve+CRC, frame,
+ *                           classify, fetch (n_phases <= 8).
+ * One object serves one host thread; objects on different streams overlap (R1 and R2 of a sample).
+ * Environment: KID_GZ_GPU_PIECE (bytes, 32768), KID_GZ_GPU_EXPAND (symbols reserved per compressed byte, 8). */
+typedef struct kid_fastq kid_fastq;
+int kid_fastq_create(const kid_db *db, kid_fastq **out);
+void kid_fastq_free(kid_fastq *f);
+int kid_fastq_prefetch_gz_file(kid_fastq *f, const char *path);
+int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads);
+int kid_fastq_classify(kid_fastq *f, kid_sample *s, int32_t *out_taxon);
+int kid_fastq_fetch(kid_fastq *f, const uint32_t *reads, size_t n, const char **data, const uint32_t **lens);
+int kid_fastq_stats(const kid_fastq *f, uint64_t *n_text, uint64_t *n_pieces, uint64_t *n_again, uint64_t *n_members,
+                    double *phase_seconds, int n_phases);
 
 #ifdef __cplusplus
 }

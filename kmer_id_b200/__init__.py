@@ -51,6 +51,7 @@ _SIGS = {
     "kid_sample_create": (_i, [_vp, C.POINTER(_vp)]),
     "kid_sample_free": (None, [_vp]),
     "kid_sample_begin": (_i, [_vp, _vp]),
+    "kid_sample_db": (_vp, [_vp]),
     "kid_classify_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "kid_classify_host": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "kid_pack_bound": (_sz, [_sz, _u64]),
@@ -82,6 +83,14 @@ _SIGS = {
     "kid_sample_read_counts": (_i, [_vp, _vp, _vp, _vp]),
     "kid_device_sync": (_i, [_i]),
     "kid_ucount_range_device": (_i, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "kid_fastq_create": (_i, [_vp, C.POINTER(_vp)]),
+    "kid_fastq_free": (None, [_vp]),
+    "kid_fastq_load_gz_file": (_i, [_vp, C.c_char_p, C.POINTER(_sz)]),
+    "kid_fastq_prefetch_gz_file": (_i, [_vp, C.c_char_p]),
+    "kid_fastq_classify": (_i, [_vp, _vp, _vp]),
+    "kid_fastq_fetch": (_i, [_vp, _vp, _sz, C.POINTER(_vp), C.POINTER(_vp)]),
+    "kid_fastq_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64),
+                            C.POINTER(C.c_double), _i]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _f = getattr(lib, _name)  # AttributeError here = the .so does not match include/kmer_id.h
@@ -95,7 +104,8 @@ KID_PACK_IMPL_BYTES = 0x100
 KID_PACK_IMPL_SWAR = 0x200
 KID_MAX_SLOTS = 4
 ERROR_NAMES = {-1: "KID_EINVAL", -2: "KID_ECUDA", -3: "KID_ENOMEM", -4: "KID_ERANGE",
-               -5: "KID_ETREE", -6: "KID_EFULL"}
+               -5: "KID_ETREE", -6: "KID_EFULL", -7: "KID_EUNSUPPORTED"}
+KID_EUNSUPPORTED = -7
 
 
 class KidError(RuntimeError):
@@ -378,3 +388,67 @@ class Sample:
     def ucount_range(self, seen: int, word0: int, n_words: int, ucount_partial, stream: int = 0):
         _check(lib.kid_ucount_range_device(self.db._h, seen, word0, n_words, _as_ptr(ucount_partial),
                                            stream or None))
+
+
+class GzFastq:
+    """A gzip FASTQ file inflated, framed and classified on the device (kid_fastq_* of include/kmer_id.h;
+    process_fqgz, newkmer_10nx.cpp:762-816).  load() returns False for a file the host reader has to take."""
+
+    PHASES = ("read", "find", "inflate", "chain", "resolve", "frame", "classify", "fetch")
+
+    def __init__(self, db: Database):
+        self.db = db
+        self._h = _vp()
+        _check(lib.kid_fastq_create(db._h, C.byref(self._h)))
+        self.n_reads = 0
+        self.why = ""
+
+    def close(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.kid_fastq_free(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def prefetch(self, path: str) -> None:
+        _check(lib.kid_fastq_prefetch_gz_file(self._h, os.fsencode(path)))
+
+    def load(self, path: str) -> bool:
+        n = _sz(0)
+        rc = lib.kid_fastq_load_gz_file(self._h, os.fsencode(path), C.byref(n))
+        if rc == KID_EUNSUPPORTED:
+            self.why = lib.kid_last_error().decode("utf-8", "replace")
+            self.n_reads = 0
+            return False
+        _check(rc)
+        self.n_reads = n.value
+        return True
+
+    def classify(self, sample: "Sample") -> np.ndarray:
+        out = np.full(self.n_reads, -2, dtype=np.int32)
+        _check(lib.kid_fastq_classify(self._h, sample._h, _np_ptr(out) if self.n_reads else None))
+        return out
+
+    def fetch(self, reads) -> list:
+        """[(header, trimmed bases)] as bytes for the given record indices"""
+        idx = np.ascontiguousarray(reads, dtype=np.uint32)
+        data, lens = _vp(), _vp()
+        _check(lib.kid_fastq_fetch(self._h, _np_ptr(idx) if idx.size else None, idx.size, C.byref(data), C.byref(lens)))
+        if idx.size == 0:
+            return []
+        ln = np.ctypeslib.as_array(C.cast(lens, C.POINTER(C.c_uint32)), shape=(2 * idx.size,)).copy()
+        total = int(ln.sum())
+        raw = C.string_at(data, total) if total else b""
+        out, at = [], 0
+        for i in range(idx.size):
+            h, b = int(ln[2 * i]), int(ln[2 * i + 1])
+            out.append((raw[at:at + h], raw[at + h:at + h + b]))
+            at += h + b
+        return out
+
+    def stats(self) -> dict:
+        a, b, c, d = _u64(), _u64(), _u64(), _u64()
+        ph = (C.c_double * 8)()
+        _check(lib.kid_fastq_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), ph, 8))
+        return {"text_bytes": a.value, "pieces": b.value, "inflated_again": c.value, "members": d.value,
+                "seconds": dict(zip(self.PHASES, [float(x) for x in ph]))}

@@ -1,7 +1,7 @@
 // kid_api.cu - the C-ABI of include/kmer_id.h: contexts, memory, streams and kernel launches.
 // No CPU fallback: every entry point needs a CUDA device and says so when there is none.
 #include "../../include/kmer_id.h"
-#include "kid_kernels.cuh"
+#include "kid_internal.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -21,7 +21,9 @@ thread_local char g_err[512] = "";
 // on or kid_device_init was called for (so that a host using GPU 3 does not wake GPU 0 for it)
 int g_host_alloc_device = 0;
 
-int fail(int code, const char *fmt, ...)
+} // namespace
+
+int kid_fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -29,82 +31,7 @@ int fail(int code, const char *fmt, ...)
     va_end(ap);
     return code;
 }
-
-#define KID_CUDA(call)                                                                            \
-    do {                                                                                          \
-        cudaError_t e_ = (call);                                                                  \
-        if (e_ != cudaSuccess)                                                                    \
-            return fail(e_ == cudaErrorMemoryAllocation ? KID_ENOMEM : KID_ECUDA, "%s: %s (%s:%d)", \
-                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                       \
-    } while (0)
-
-struct DeviceGuard { // make `device` current for the call, restore the caller's device after
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int device)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
-        ok = cudaSetDevice(device) == cudaSuccess;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-struct HostSlot { // one asynchronous slot: a stream and its device staging buffers
-    cudaStream_t stream = nullptr;
-    uint8_t *seq = nullptr, *qual = nullptr; // text batches
-    uint64_t *off = nullptr;
-    uint32_t *words = nullptr;               // packed batch: copied from the host or written by kid_pack_kernel
-    uint2 *meta = nullptr;
-    int32_t *out_taxon = nullptr;
-    uint32_t *out_span = nullptr;
-    size_t cap_bytes = 0, cap_reads = 0, cap_words = 0;
-    bool has_qual = false;
-    uint32_t *dn_codes = nullptr, *dn_boff = nullptr, *dn_flags = nullptr, *dn_inv = nullptr; // dense batches
-    size_t dn_cap_codes = 0, dn_cap_reads = 0, dn_cap_inv = 0;
-};
-
-} // namespace
-
-struct kid_db {
-    int device = 0;
-    int n_taxa = 0;
-    int layout = KID_LAYOUT_MINIMIZER;
-    int log2_sectors = 0;
-    int sm_count = 148;
-    int max_probe = 0;
-    int sub_bits = 2;           // layout M: log2(sectors per minimizer-addressed group)
-    int mm = 16;                // layout M: minimizer length (16, or 20 for very large databases)
-    unsigned flags = 0;
-    uint64_t n_sectors = 0;     // addressable home sectors of 32 bytes (K: 4 slots each, M: 3 entries each)
-    uint64_t total_sectors = 0; // n_sectors + slack (clusters run past the last home sector, no wrap)
-    uint64_t *slots = nullptr;  // layout K
-    uint4 *entries = nullptr;   // layout M
-    uint2 *tree = nullptr;
-    uint64_t n_distinct = 0, n_displaced = 0;
-
-    uint64_t n_slots() const { return (layout == KID_LAYOUT_KEYHASH ? 4 : KID2_SLOTS_PER_SECTOR) * total_sectors; }
-    const void *table_ptr() const { return layout == KID_LAYOUT_KEYHASH ? (const void *)slots : (const void *)entries; }
-    KidTableView table_view() const { return KidTableView{ slots, n_sectors - 1, 60 - log2_sectors }; }
-    Kid2TableView table_view2() const { return Kid2TableView{ entries, n_sectors - 1, 32 - (log2_sectors - sub_bits), max_probe, sub_bits, mm }; }
-    KidTreeView tree_view() const { return KidTreeView{ tree, n_taxa }; }
-};
-
-struct kid_sample {
-    const kid_db *db = nullptr;
-    int *gcount = nullptr, *ucount = nullptr;
-    uint32_t *seen = nullptr;      // the bitmap in use (own_seen or a caller-provided buffer)
-    uint32_t *own_seen = nullptr;  // what this object allocated
-    uint64_t n_words = 0;
-    unsigned long long *counters = nullptr;
-    cudaEvent_t begin_ev = nullptr;
-    HostSlot slot[KID_MAX_SLOTS];
-    HostSlot dev; // scratch of kid_classify_device (packed form of a text batch); no stream of its own
-    size_t chunk_reads = (size_t)1 << 18;
-    uint64_t h2d = 0, d2h = 0;
-};
+#define fail kid_fail
 
 extern "C" {
 
@@ -486,6 +413,8 @@ void kid_sample_free(kid_sample *s)
     delete s;
 }
 
+const kid_db *kid_sample_db(const kid_sample *s) { return s ? s->db : nullptr; }
+
 int kid_sample_begin(kid_sample *s, void *stream_)
 {
     if (!s) return fail(KID_EINVAL, "kid_sample_begin: s is NULL");
@@ -523,23 +452,6 @@ static KidClassifyParams make_params(kid_sample *s, const uint8_t *seq, const ui
     p.seen = s->seen;
     p.counters = s->counters;
     p.accept_u = (s->db->flags & KID_DB_ACCEPT_U) != 0;
-    return p;
-}
-
-static KidPackedParams make_packed_params(kid_sample *s, const uint32_t *words, const uint2 *meta, uint32_t bias,
-                                           size_t n, int32_t *out_taxon)
-{
-    KidPackedParams p;
-    p.table2 = s->db->table_view2();
-    p.tree = s->db->tree_view();
-    p.words = words;
-    p.meta = meta;
-    p.word_bias = bias;
-    p.n_reads = n;
-    p.out_taxon = out_taxon;
-    p.gcount = s->gcount;
-    p.seen = s->seen;
-    p.counters = s->counters;
     return p;
 }
 
@@ -612,7 +524,7 @@ static int pack_and_scan(kid_sample *s, HostSlot &h, const uint8_t *seq, const u
     pp.out_span = out_span;
     pp.accept_u = (s->db->flags & KID_DB_ACCEPT_U) != 0;
     KID_CUDA(kid_launch_pack(pp, s->db->sm_count, stream));
-    KidPackedParams p = make_packed_params(s, h.words, h.meta, 0, n, out_taxon);
+    KidPackedParams p = kid_make_packed_params(s, h.words, h.meta, 0, n, out_taxon);
     KID_CUDA(kid_launch_classify3(p, s->db->sm_count, stream));
     return KID_OK;
 }
@@ -678,7 +590,7 @@ int kid_classify_packed_device(kid_sample *s, const uint32_t *words, const uint3
     if (s->db->layout != KID_LAYOUT_MINIMIZER)
         return fail(KID_EINVAL, "packed batches need the default table layout (not KID_DB_LAYOUT_KEYHASH)");
     DeviceGuard guard(s->db->device);
-    KidPackedParams p = make_packed_params(s, words, reinterpret_cast<const uint2 *>(meta), 0, n_reads, out_taxon);
+    KidPackedParams p = kid_make_packed_params(s, words, reinterpret_cast<const uint2 *>(meta), 0, n_reads, out_taxon);
     KID_CUDA(kid_launch_classify3(p, s->db->sm_count, (cudaStream_t)stream));
     return KID_OK;
 }
@@ -752,7 +664,7 @@ static int submit_packed(kid_sample *s, HostSlot &h, const uint32_t *words, uint
     if (nw) KID_CUDA(cudaMemcpyAsync(h.words, words + (wa - word0), sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, h.stream));
     KID_CUDA(cudaMemcpyAsync(h.meta, meta + 2 * r0, sizeof(uint2) * (n + 1), cudaMemcpyHostToDevice, h.stream));
     __atomic_fetch_add(&s->h2d, sizeof(uint32_t) * nw + sizeof(uint2) * (n + 1), __ATOMIC_RELAXED);
-    KidPackedParams p = make_packed_params(s, h.words, h.meta, wa, n, out_taxon ? h.out_taxon : nullptr);
+    KidPackedParams p = kid_make_packed_params(s, h.words, h.meta, wa, n, out_taxon ? h.out_taxon : nullptr);
     KID_CUDA(kid_launch_classify3(p, s->db->sm_count, h.stream));
     if (out_taxon) {
         KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));
@@ -832,7 +744,7 @@ static int submit_dense(kid_sample *s, HostSlot &h, const uint32_t *codes, const
     ep.words = h.words;
     ep.meta = h.meta;
     KID_CUDA(kid_launch_expand(ep, s->db->sm_count, h.stream));
-    KidPackedParams p = make_packed_params(s, h.words, h.meta, 0, n, out_taxon ? h.out_taxon : nullptr);
+    KidPackedParams p = kid_make_packed_params(s, h.words, h.meta, 0, n, out_taxon ? h.out_taxon : nullptr);
     KID_CUDA(kid_launch_classify3(p, s->db->sm_count, h.stream));
     if (out_taxon) {
         KID_CUDA(cudaMemcpyAsync(out_taxon + r0, h.out_taxon, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h.stream));

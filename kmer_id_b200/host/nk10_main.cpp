@@ -27,6 +27,7 @@
 #include <fstream>
 #include <condition_variable>
 #include <iostream>
+#include <map>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -67,14 +68,120 @@ struct SavedRead { // a _reads.txt record of the R2 file, held back until R1 is 
     std::string text; // ">taxon:acc\nbases\n"
 };
 
+// ---- gz FASTQ read on the device (kid_fastq_*, include/kmer_id.h): the file's compressed bytes go to one
+// GPU, which inflates, frames, trims and classifies them; the host gets the per-read taxa and asks for the
+// text of the few reads _reads.txt wants.  KID_GPU_INGEST=0 keeps every file on the host reader.
+struct GpuReader {
+    kid_fastq *fq = nullptr;
+    int32_t *taxon = nullptr; // page-locked
+    size_t cap = 0;
+};
+
+GpuReader &gpu_reader(kid_sample *smp, int which)
+{
+    static std::mutex mu;
+    static std::map<std::pair<kid_sample *, int>, GpuReader> readers; // live until exit, like the samples
+    std::lock_guard<std::mutex> lk(mu);
+    GpuReader &r = readers[{ smp, which }];
+    if (!r.fq && kid_fastq_create(kid_sample_db(smp), &r.fq) != 0) die(1, kid_last_error());
+    return r;
+}
+
+// false: the file is one for the host reader (nothing has been counted)
+bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std::string &next_path, SampleState &st,
+                  std::ostream *outread, std::vector<SavedRead> *saved, bool stats)
+{
+    static const bool enabled = !(getenv("KID_GPU_INGEST") && atoi(getenv("KID_GPU_INGEST")) == 0);
+    if (!enabled) return false;
+    GpuReader &gr = gpu_reader(smp, which);
+    const double t_begin = now();
+    size_t n = 0;
+    const int rc = kid_fastq_load_gz_file(gr.fq, path.c_str(), &n);
+    if (rc == KID_EUNSUPPORTED) {
+        if (stats) fprintf(stderr, "[nk10] %s\n", kid_last_error());
+        return false;
+    }
+    if (rc != 0) die(1, kid_last_error());
+    // the same file of the next sample is read (and copied to the device) while this one is classified and written
+    if (!next_path.empty() && kid_fastq_prefetch_gz_file(gr.fq, next_path.c_str()) != 0) die(1, kid_last_error());
+    if (n > gr.cap) {
+        kid_host_free(gr.taxon);
+        gr.taxon = nullptr;
+        gr.cap = n + n / 8 + 1024;
+        void *p = nullptr;
+        if (kid_host_alloc(&p, sizeof(int32_t) * gr.cap) != 0) die(1, kid_last_error());
+        gr.taxon = (int32_t *)p;
+    }
+    const double t_loaded = now();
+    if (kid_fastq_classify(gr.fq, smp, gr.taxon) != 0) die(1, kid_last_error());
+    const double t_classified = now();
+    // the reads process_read would write (:608-611): fewer than SAVENUM of their taxon came before them
+    std::vector<uint32_t> pick;
+    for (size_t r = 0; r < n; r++) {
+        const int fin = gr.taxon[r];
+        if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
+        if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) pick.push_back((uint32_t)r);
+        st.gcount_host[(size_t)fin]++;
+        st.tct++;
+    }
+    const char *data = nullptr;
+    const uint32_t *lens = nullptr;
+    if (kid_fastq_fetch(gr.fq, pick.data(), pick.size(), &data, &lens) != 0) die(1, kid_last_error());
+    // ">taxon:header\nbases\n" per read (the bytes of :610), assembled in one buffer
+    size_t at = 0, total = 0;
+    for (size_t i = 0; i < pick.size(); i++) total += lens[2 * i] + lens[2 * i + 1] + 16;
+    std::string text;
+    text.reserve(total);
+    for (size_t i = 0; i < pick.size(); i++) {
+        const int fin = gr.taxon[pick[i]];
+        const char *name = data + at, *bases = name + lens[2 * i];
+        const size_t nlen = lens[2 * i], blen = lens[2 * i + 1];
+        at += nlen + blen;
+        char num[16];
+        int nd = 0;
+        for (int v = fin; v > 0; v /= 10) num[nd++] = (char)('0' + v % 10); // fin > 1
+        const size_t rec0 = text.size();
+        text.push_back('>');
+        while (nd) text.push_back(num[--nd]);
+        text.push_back(':');
+        text.append(name, nlen);
+        text.push_back('\n');
+        text.append(bases, blen);
+        text.push_back('\n');
+        if (saved) {
+            SavedRead sr;
+            sr.taxon = fin;
+            sr.text = text.substr(rec0);
+            saved->push_back(std::move(sr));
+        }
+    }
+    if (outread) outread->write(text.data(), (std::streamsize)text.size());
+    if (outread) outread->flush();
+    if (stats) {
+        fprintf(stderr, "[nk10] %s: load %.3f classify %.3f pick+fetch+write %.3f s (%zu reads written)\n", path.c_str(), t_loaded - t_begin,
+                t_classified - t_loaded, now() - t_classified, pick.size());
+        uint64_t text = 0, pieces = 0, again = 0, members = 0;
+        double ph[8] = { 0 };
+        kid_fastq_stats(gr.fq, &text, &pieces, &again, &members, ph, 8);
+        fprintf(stderr, "[nk10] %s on the device: %zu reads, %llu bytes of text in %llu pieces (%llu inflated again), %llu members; "
+                        "read %.3f find %.3f inflate %.3f chain %.3f resolve %.3f frame %.3f classify %.3f fetch %.3f s\n",
+                path.c_str(), n, (unsigned long long)text, (unsigned long long)pieces, (unsigned long long)again,
+                (unsigned long long)members, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+    }
+    return true;
+}
+
 // Classify one FASTQ file batch by batch on the given shards (one kid_sample per GPU), using their
 // slots slot_base, slot_base+1.  direct = R1: append to _reads.txt exactly as process_read :608-614
 // does.  Otherwise (R2, running concurrently with R1) keep the first SAVENUM records per taxon in
 // stream order; the caller writes those that the reference would have written once R1's per-taxon
 // counts are known.
-void run_file(kid_sample *const *smps, int n_smps, int slot_base, const std::string &path, SampleState &st,
-              std::ostream *outread, std::vector<SavedRead> *saved, unsigned concurrent_files)
+void run_file(kid_sample *const *smps, int n_smps, int slot_base, const std::string &path, const std::string &next_path,
+              SampleState &st, std::ostream *outread, std::vector<SavedRead> *saved, unsigned concurrent_files, bool stats)
 {
+    // the whole file on one GPU: R1 on the first shard, R2 (running next to it) on the second if there is one
+    const int which = slot_base ? 1 : 0;
+    if (run_file_gpu(smps[which % n_smps], which, path, next_path, st, outread, saved, stats)) return;
     // R1 and R2 (and, with KID_MULTI_MODE=samples, several samples) are inflated at the same time: share the cores
     ReadBatchReader reader(ReadFormat::GzFastq, path, (size_t)1 << 18, kBatchBytes, pipeline_batches(n_smps),
                            default_gz_threads(concurrent_files));
@@ -110,9 +217,11 @@ void run_file(kid_sample *const *smps, int n_smps, int slot_base, const std::str
 // One sample (main():1015-1045) on the shards smps[0..n): R1 then R2 (KID_SERIAL) or both at once.
 // `log` receives what the reference prints for this sample.  counts() merges the shards.
 template <class Counts>
-void process_sample(kid_sample *const *smps, int n_smps, const std::string &dname, const std::string &s, bool serial,
-                    unsigned concurrent_samples, std::ostream &log, Counts &&counts, bool stats, GpuSet *stats_set)
+void process_sample(kid_sample *const *smps, int n_smps, const std::string &dname, const std::string &s, const std::string &next,
+                    bool serial, unsigned concurrent_samples, std::ostream &log, Counts &&counts, bool stats, GpuSet *stats_set)
 {
+    // `next`: the sample after this one if it is known already (its files are read ahead), else empty
+    const std::string next1 = next.empty() ? std::string() : dname + next + e1, next2 = next.empty() ? std::string() : dname + next + e2;
     const double ts = now();
     SampleState st, st2;
     st.gcount_host.assign((size_t)MAXTAR, 0);
@@ -122,16 +231,16 @@ void process_sample(kid_sample *const *smps, int n_smps, const std::string &dnam
     std::ofstream outread(trname.c_str(), std::ofstream::out | std::ofstream::trunc);
     long long tct_total = 0;
     if (serial) {
-        run_file(smps, n_smps, 0, dname + s + e1, st, &outread, nullptr, concurrent_samples);
+        run_file(smps, n_smps, 0, dname + s + e1, std::string(), st, &outread, nullptr, concurrent_samples, stats);
         log << st.tct << " reads loaded" << std::endl; // :1030
-        run_file(smps, n_smps, 0, dname + s + e2, st, &outread, nullptr, concurrent_samples);
+        run_file(smps, n_smps, 0, dname + s + e2, next1, st, &outread, nullptr, concurrent_samples, stats);
         tct_total = st.tct;
     } else {
         // R1 and R2 are inflated, parsed and classified concurrently into the SAME accumulators (gcount and
         // the seen flags are order independent), each thread on its own pair of slots
         std::vector<SavedRead> saved;
-        std::thread t2([&] { run_file(smps, n_smps, kPipelineSlots, dname + s + e2, st2, nullptr, &saved, 2 * concurrent_samples); });
-        run_file(smps, n_smps, 0, dname + s + e1, st, &outread, nullptr, 2 * concurrent_samples);
+        std::thread t2([&] { run_file(smps, n_smps, kPipelineSlots, dname + s + e2, next2, st2, nullptr, &saved, 2 * concurrent_samples, stats); });
+        run_file(smps, n_smps, 0, dname + s + e1, next1, st, &outread, nullptr, 2 * concurrent_samples, stats);
         log << st.tct << " reads loaded" << std::endl; // :1030
         t2.join();
         // an R2 read is written iff fewer than SAVENUM reads of its taxon came before it, R1 first
@@ -219,9 +328,10 @@ int main(int argc, char *argv[])
     const bool by_sample = n_gpus > 1 && mm && std::string(mm) == "samples";
     if (!by_sample) {
         // every sample on all GPUs: its batches are dealt to the GPUs, one exchange at sample end
-        for (const std::string &s : fnames) {
+        for (size_t i = 0; i < fnames.size(); i++) {
+            const std::string &s = fnames[i];
             if (!gpus.begin(msg)) die(1, msg); // :1017-1019
-            process_sample(gpus.samples.data(), n_gpus, dname, s, serial, 1, std::cout,
+            process_sample(gpus.samples.data(), n_gpus, dname, s, i + 1 < fnames.size() ? fnames[i + 1] : std::string(), serial, 1, std::cout,
                            [&](int32_t *g, int32_t *u) { if (!gpus.counts(g, u, MAXTAR, msg)) die(1, msg); }, stats, &gpus);
         }
     } else {
@@ -245,7 +355,7 @@ int main(int argc, char *argv[])
                     }
                     if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error());
                     std::ostringstream log;
-                    process_sample(&smp, 1, dname, fnames[i], serial, (unsigned)n_gpus, log,
+                    process_sample(&smp, 1, dname, fnames[i], std::string(), serial, (unsigned)n_gpus, log,
                                    [&](int32_t *gc, int32_t *uc) { if (kid_sample_counts(smp, gc, uc, nullptr) != 0) die(1, kid_last_error()); },
                                    stats, nullptr);
                     {
