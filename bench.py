@@ -558,12 +558,17 @@ def files_e2e(args, n_gpus=1):
         if r.returncode != 0:
             return {"error": "nk10 exited %d: %s" % (r.returncode, r.stderr[-300:])}
         per_sample = [float(x) for x in re.findall(r"\[nk10\] s\d+: \d+ reads, \d+ lookups, \d+ hits in ([0-9.]+) s", r.stderr)]
+        on_device_files = len(re.findall(r"on the device: \d+ reads", r.stderr))
+        on_device = on_device_files == 2 * n_samples
         m = re.search(r"\[nk10\] parse db ([0-9.]+) s, build table ([0-9.]+) s, total ([0-9.]+) s", r.stderr)
         med = statistics.median(per_sample)
         return {"value": pairs / med, "unit": UNIT,
                 "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, MEDIAN of %d samples in one "
-                        "process (inflate on all host cores, parse + trim + pack, classify); probe DB parsed from gz text"
-                        % n_samples,
+                        "process (%s); probe DB parsed from gz text"
+                        % (n_samples, "compressed bytes to the GPU: inflate, line framing, trim, pack and classify in kernels, "
+                                      "read-ahead of the next sample" if on_device else
+                                      "inflate on all host cores, parse + trim + pack on the host, classify on the GPU"),
+                "reader": "device" if on_device else "host", "files_on_device": on_device_files,
                 "n_gpus": n_gpus, "mode": (re.findall(r"GPU\(s\)(.*)", r.stderr) or [""])[0].strip(", "),
                 "pairs_per_sample": pairs, "sample_s": per_sample,
                 "first_sample_pairs_per_s": pairs / per_sample[0], "best_sample_pairs_per_s": pairs / min(per_sample),

@@ -281,7 +281,13 @@ KIDZ_HD bool code_is_acceptable(const uint8_t *lens, int n, CodeKind kind)
     return !(left > 0 && !(kind == kCodeDist && used == 1 && maxlen == 1));
 }
 
-KIDZ_HD uint32_t peek32(const uint32_t *w, uint64_t bit) // 32 bits from any bit position
+KIDZ_HD uint32_t peek32(const uint32_t *w, uint32_t bit) // 32 bits from any bit position below 2^32
+{
+    const uint32_t i = bit >> 5, sh = bit & 31u;
+    const uint64_t v = (uint64_t)w[i] | ((uint64_t)w[i + 1] << 32);
+    return (uint32_t)(v >> sh);
+}
+KIDZ_HD uint32_t peek32(const uint32_t *w, uint64_t bit)
 {
     const uint64_t i = bit >> 5;
     const uint32_t sh = (uint32_t)(bit & 31);
@@ -294,8 +300,10 @@ KIDZ_HD bool block_start_bits_plausible(uint32_t v)
 {
     return (v & 6u) == 4u && ((v >> 3) & 31u) <= 29u && ((v >> 8) & 31u) <= 29u;
 }
-// ...second: a COMPLETE code-length code.
-KIDZ_HD bool block_start_cl_complete(const uint32_t *w, uint64_t bit, uint32_t v)
+// ...second: a COMPLETE code-length code.  (BitPos: uint64_t, or uint32_t for positions relative to a
+// piece - the block finder's inner loops stay in 32-bit arithmetic.)
+template <class BitPos>
+KIDZ_HD bool block_start_cl_complete(const uint32_t *w, BitPos bit, uint32_t v)
 {
     const int ncl = (int)((v >> 13) & 15u) + 4;
     uint32_t kraft = 0;

@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t queue_drop32(uint32_t *q, uint32_t qn, uint3
 }
 
 __global__ void __launch_bounds__(kFindWarps * 32)
-kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_t n_pieces, uint64_t *start_bit)
+kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_t n_pieces, bool text_only, uint64_t *start_bit)
 {
     extern __shared__ uint16_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -82,26 +82,36 @@ kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_
     uint16_t *wmem = smem + warp * kFindWarpEntries;
     Tab<32> tab{ wmem + lane };
     uint32_t *q1 = reinterpret_cast<uint32_t *>(wmem + 32 * kFindTabEntries), *q2 = q1 + 64;
-    const uint64_t from = (uint64_t)k * piece_bytes * 8;
-    const uint64_t to = min(size, ((uint64_t)k + 1) * piece_bytes) * 8;
+    const uint64_t from = (uint64_t)k * piece_bytes * 8; // a multiple of 32: piece_bytes is one of 4
+    const uint32_t *wp = w + (from >> 5);
+    const uint32_t n_bits = (uint32_t)(min(size, ((uint64_t)k + 1) * piece_bytes) * 8 - from);
     uint32_t n1 = 0, n2 = 0;
     uint64_t found = ~0ull;
-    for (uint64_t base = from; found == ~0ull; base += 32) {
-        const bool more = base < to;
+    uint32_t mine = 0, after = 0; // 32 words of the piece, one per lane, and the word behind them
+    for (uint32_t it = 0; found == ~0ull; it++) { // positions 32 it .. 32 it + 31, one per lane
+        const bool more = it * 32u < n_bits;
         if (more) {
-            const uint64_t b = base + lane;
-            n1 = queue_push(q1, n1, b < to && block_start_bits_plausible(peek32(w, b)), (uint32_t)(b - from), lane);
+            if ((it & 31u) == 0) {
+                mine = wp[it + lane];
+                after = wp[it + 32u];
+            }
+            const uint32_t lo = __shfl_sync(kFull, mine, (int)(it & 31u));
+            const uint32_t nx = __shfl_sync(kFull, mine, (int)((it + 1u) & 31u));
+            const uint32_t v = __funnelshift_r(lo, (it & 31u) == 31u ? after : nx, lane);
+            const uint32_t r = it * 32u + lane;
+            n1 = queue_push(q1, n1, r < n_bits && block_start_bits_plausible(v), r, lane);
         }
+        if (n1 < 32 && more) continue;
         for (;;) { // drain: q1 below 32 entries (empty at the end of the piece), q2 likewise
             while ((n1 >= 32 || (!more && n1 > 0)) && n2 < 32) {
                 const uint32_t c = lane < n1 ? q1[lane] : 0u;
-                const bool pass = lane < n1 && block_start_cl_complete(w, from + c, peek32(w, from + c));
+                const bool pass = lane < n1 && block_start_cl_complete(wp, c, peek32(wp, c));
                 n2 = queue_push(q2, n2, pass, c, lane); // <= 63
                 n1 = queue_drop32(q1, n1, lane);
             }
             while (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
                 const uint32_t c = lane < n2 ? q2[lane] : 0u;
-                const bool ok = lane < min(n2, 32u) && is_block_start(w, from + c, tab, true);
+                const bool ok = lane < min(n2, 32u) && is_block_start(w, from + c, tab, text_only);
                 const unsigned m = __ballot_sync(kFull, ok);
                 if (m) {
                     found = from + __shfl_sync(kFull, c, __ffs(m) - 1);
@@ -189,33 +199,29 @@ __device__ __forceinline__ int warp_symbols(const uint32_t *w, uint64_t size_bit
                 code = kCopyFlag | (dist - 1u);
             }
         }
-        const uint32_t nxt = lane + bits; // where the next token starts, relative to bp (<= 31 + 48)
-        // the chain of real tokens from lane 0
-        uint32_t chain = 0, cur = 0;
-        bool eob = false;
+        // the chain of real tokens from lane 0: one shuffle per token brings where the next one starts
+        // (relative to bp, <= 31 + 48), its kind and how many positions it writes
+        const uint32_t link = (lane + bits) | (kind << 7) | (outlen << 9);
+        uint32_t cur = 0, total = 0;
+        int32_t at = 0;
+        bool on = false, eob = false;
         while (cur < 32u) {
-            const uint32_t kd = __shfl_sync(kFull, kind, (int)cur);
+            const uint32_t l = __shfl_sync(kFull, link, (int)cur);
+            const uint32_t kd = (l >> 7) & 3u;
             if (kd == 3u) break;
-            chain |= 1u << cur;
-            cur = __shfl_sync(kFull, nxt, (int)cur);
+            if (lane == cur) {
+                on = true;
+                at = pos + (int32_t)total;
+            }
+            total += l >> 9;
+            cur = l & 127u;
             if (kd == 2u) {
                 eob = true;
                 break;
             }
         }
-        if (chain == 0) return kRoundSlowToken; // the token at bp itself needs the plain decoder
-        // where every token of the chain writes
-        const bool on = (chain >> lane) & 1u;
-        const uint32_t mine = on ? outlen : 0u;
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(kFull, incl, d);
-            if (lane >= (uint32_t)d) incl += up;
-        }
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        if (total == 0 && !eob && cur == 0) return kRoundSlowToken; // the token at bp itself needs the plain decoder
         if (total > (uint32_t)(cap - pos)) return kRoundOverflow;
-        const int32_t at = pos + (int32_t)(incl - mine);
         const bool match = on && kind == 1u;
         // a match may not reach before the member / before any history
         if (__any_sync(kFull, match && (int32_t)((code & 0x7fffu) + 1u) > at - floor)) return kRoundBad;
@@ -465,7 +471,19 @@ kidz_crc_kernel(const uint8_t *text, uint64_t n_text, const Member *members, uin
         if (mend <= a) { m++; continue; } // an empty member
         const uint64_t b = min(cend, mend);
         uint32_t crc = 0xffffffffu;
-        for (uint64_t i = a; i < b; i++) crc = tab[(crc ^ text[i]) & 0xffu] ^ (crc >> 8);
+        uint64_t i = a;
+        if ((a & 15u) == 0) // the usual case, a whole chunk inside one member: 16 bytes per load
+            for (; i + 16 <= b; i += 16) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(text + i);
+                const uint32_t wv[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t x = wv[k];
+#pragma unroll
+                    for (int j = 0; j < 4; j++, x >>= 8) crc = tab[(crc ^ x) & 0xffu] ^ (crc >> 8);
+                }
+            }
+        for (; i < b; i++) crc = tab[(crc ^ text[i]) & 0xffu] ^ (crc >> 8);
         crc ^= 0xffffffffu;
         atomicXor(acc + m, crc_mulmod(crc_x8n(mend - b, pow2), crc));
         a = b;
@@ -786,7 +804,8 @@ struct GzLoader {
     PinBuf stage[2];
     DevBuf gz;
     uint64_t size = 0, first_block_bit = 0;
-    const char *why = ""; // with KID_EUNSUPPORTED
+    bool text_only = false; // the file's first block codes no byte below 9 or from 128 on: see is_block_start
+    const char *why = "";   // with KID_EUNSUPPORTED
 
     int open_streams()
     {
@@ -807,7 +826,7 @@ struct GzLoader {
         size = (uint64_t)sb.st_size;
         if (size < 18) { why = "shorter than a gzip member"; return KID_EUNSUPPORTED; }
         if (size >= ((uint64_t)1 << 36)) { why = "larger than 64 GiB"; return KID_EUNSUPPORTED; }
-        const size_t gz_cap = (size_t)((size + 3) & ~3ull) + 128;
+        const size_t gz_cap = (size_t)((size + 3) & ~3ull) + 1024; // the block finder loads whole 128-byte rows
         KID_CUDA(gz.reserve(gz_cap));
         const size_t tail0 = (size_t)size & ~(size_t)3; // zero padding behind the file: the bit readers run a few words past it
         KID_CUDA(cudaMemsetAsync(gz.as<uint8_t>() + tail0, 0, gz_cap - tail0, stream));
@@ -830,6 +849,12 @@ struct GzLoader {
                 const uint64_t hl = gzip_header_len(dst, std::min<uint64_t>(size, want), 0);
                 if (!hl) { why = "no gzip header"; return KID_EUNSUPPORTED; }
                 first_block_bit = hl * 8;
+                // the block finder's text-only filter is used if the file's own first block passes it
+                text_only = false;
+                if (want >= hl + 1024 && (peek32(reinterpret_cast<const uint32_t *>(dst), first_block_bit) & 6u) == 4u) {
+                    uint16_t tabmem[kFindTabEntries];
+                    text_only = is_block_start(reinterpret_cast<const uint32_t *>(dst), first_block_bit, Tab<1>{ tabmem }, true);
+                }
             }
             KID_CUDA(cudaMemcpyAsync(gz.as<uint8_t>() + done, dst, want, cudaMemcpyHostToDevice, stream));
             KID_CUDA(cudaEventRecord(ev[which], stream));
@@ -1026,7 +1051,7 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     const uint32_t *w = ld->gz.as<uint32_t>();
     if (n_pieces > 1) {
         const unsigned blocks = (unsigned)((n_pieces - 1 + kFindWarps - 1) / kFindWarps);
-        kidz_find_kernel<<<blocks, kFindWarps * 32, kFindWarps * kFindWarpEntries * 2, st>>>(w, size, P, (uint32_t)n_pieces, f->start.as<uint64_t>());
+        kidz_find_kernel<<<blocks, kFindWarps * 32, kFindWarps * kFindWarpEntries * 2, st>>>(w, size, P, (uint32_t)n_pieces, ld->text_only, f->start.as<uint64_t>());
         KID_COUNT_LAUNCH();
         KID_CUDA(cudaGetLastError());
     }

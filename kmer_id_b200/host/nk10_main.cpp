@@ -7,8 +7,9 @@
 // libkmerid_b200.so (include/kmer_id.h); there is no CPU classification path in this program.
 //
 // Extras that do not change the contract: all visible GPUs are used (KID_GPUS=<k> limits them,
-// KID_DEVICE=<n> pins one; KID_MULTI_MODE=samples deals whole samples to the GPUs instead of splitting
-// every sample over all of them), KID_STATS=1 prints phase
+// KID_DEVICE=<n> pins one; whole samples are dealt to the GPUs when there are several, a single sample is
+// split over all of them: KID_MULTI_MODE=samples|reads forces either), gz FASTQ files are inflated and
+// framed on the GPU (KID_GPU_INGEST=0: on the host), KID_STATS=1 prints phase
 // timings to stderr, and the parsed probe list is cached next to probes10.txt.gz as
 // probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
 #include "../../include/kmer_id.h"
@@ -324,8 +325,11 @@ int main(int argc, char *argv[])
     // KID_SERIAL=1 processes R1 then R2 on one thread, like the reference.
     const bool serial = getenv("KID_SERIAL") != nullptr;
     const int n_gpus = (int)gpus.devices.size();
+    // several GPUs: whole samples are dealt to the GPUs when there are several samples (no exchange at all, and
+    // with the device-side reader every GPU inflates its own files); a lone sample is split over all GPUs.
+    // KID_MULTI_MODE=samples / reads forces one or the other.
     const char *mm = getenv("KID_MULTI_MODE");
-    const bool by_sample = n_gpus > 1 && mm && std::string(mm) == "samples";
+    const bool by_sample = n_gpus > 1 && (mm ? std::string(mm) == "samples" : fnames.size() > 1);
     if (!by_sample) {
         // every sample on all GPUs: its batches are dealt to the GPUs, one exchange at sample end
         for (size_t i = 0; i < fnames.size(); i++) {

@@ -29,14 +29,19 @@ def _run_both(work, fq):
     # default = R1 and R2 classified concurrently on two samples; KID_SERIAL=1 = one after the other;
     # KID_GZ_*: force the multi-threaded inflater (host/pgz.cpp) onto these small files / switch it off
     envs = [{}, {"KID_SERIAL": "1"}, {"KID_GZ_MIN_BYTES": "0", "KID_GZ_PIECE_BYTES": "8192", "KID_NO_CACHE": "1"},
-            {"KID_GZ_THREADS": "1"}, {"KID_PARSE_THREADS": "0"}, {"KID_GPUS": "1"}]
+            {"KID_GZ_THREADS": "1"}, {"KID_PARSE_THREADS": "0"}, {"KID_GPUS": "1"},
+            # the host reader for every file (by default ordinary gz FASTQ files are inflated and framed on the GPU),
+            # and the device reader with small pieces so that these small files are cut into many
+            {"KID_GPU_INGEST": "0"}, {"KID_GPU_INGEST": "0", "KID_SERIAL": "1"}, {"KID_GZ_GPU_PIECE": "4096"}]
     import kmer_id_b200 as kid
     if kid.device_count() >= 2:
         # several GPUs in the C++ host (the default {} already uses every visible GPU): each sample's
         # batches dealt to the GPUs with the NCCL / host-sum exchange at sample end, and whole samples
         # dealt to the GPUs
         envs += [{"KID_GPUS": "2"}, {"KID_GPUS": "2", "KID_NO_NCCL": "1"}, {"KID_GPUS": "2", "KID_SERIAL": "1"},
-                 {"KID_MULTI_MODE": "samples"}, {"KID_GPUS": "2", "KID_MULTI_MODE": "samples", "KID_SERIAL": "1"}]
+                 {"KID_MULTI_MODE": "samples"}, {"KID_GPUS": "2", "KID_MULTI_MODE": "samples", "KID_SERIAL": "1"},
+                 {"KID_MULTI_MODE": "reads"}, {"KID_GPUS": "2", "KID_MULTI_MODE": "reads", "KID_GPU_INGEST": "0"},
+                 {"KID_GPUS": "2", "KID_MULTI_MODE": "reads", "KID_NO_NCCL": "1", "KID_GPU_INGEST": "0"}]
     for env in envs:
         r_gpu = subprocess.run([NK_GPU, fq if fq.endswith("/") else fq + "/"], cwd=work, capture_output=True,
                                timeout=600, env=dict(os.environ, **env))

@@ -8,7 +8,7 @@ for i in 0 1 2 3 4; do $R/tools/kid_synth reads --golden $R/tests/golden/b10 --o
 KID_STATS=1 KID_GPUS=1 KID_GPU_INGEST=0 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ > $W/host.out 2> $W/host.err; echo "host reader rc=$?"
 grep "reads," $W/host.err
 mkdir -p $W/keep; mv $W/fq/*_result.txt $W/fq/*_reads.txt $W/keep/
-for P in 32768 16384; do
+for P in 32768; do
   echo "== piece $P"
   KID_GZ_GPU_PIECE=$P KID_STATS=1 KID_GPUS=1 KID_GZ_GPU_TIMING=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ > $W/gpu.out 2> $W/gpu.err; echo "device reader rc=$?"
   grep -v "^\[nk10\] parse\|cached" $W/gpu.err | tail -n +10 | sed -e 's/.*pieces (/(/' -e 's/.*fastq.gz: /: /' | cut -c1-300
@@ -19,5 +19,8 @@ echo "== untimed"
 KID_STATS=1 KID_GPUS=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ 2>&1 >/dev/null | grep "reads,\|total"
 cp $W/gpu.err $R/gpurun_out/z_gpu.err
 cd $R
-timeout 600 python -m pytest tests/test_nk10_dropin.py -m gpu -q --tb=short -x > gpurun_out/gputests_z.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gputests_z.log
+timeout 600 python -m pytest tests/test_gpu_ingest.py tests/test_nk10_dropin.py -m gpu -q --tb=short -x > gpurun_out/gputests_z.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gputests_z.log
 tail -n 4 gpurun_out/gputests_z.log
+# per-kernel times of one nk10 run on one sample (serialised by ncu: shares, not absolutes)
+cd $W; rm -f $W/fq/s1_* $W/fq/s2_* $W/fq/s3_* $W/fq/s4_*
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $R/gpurun_out/z_launches.csv env KID_GPUS=1 $R/kmer_id_b200/bin/nk10 $W/fq/ > /dev/null 2>&1; echo "ncu rc=$?"
