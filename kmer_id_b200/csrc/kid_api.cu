@@ -59,6 +59,9 @@ int kid_device_init(int device)
     if (e != cudaSuccess) return fail(KID_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
     if (device < 0 || device >= c) return fail(KID_EINVAL, "kid_device_init: device %d of %d", device, c);
     DeviceGuard guard(device);
+    // KID_SYNC_BLOCKING=1: host threads sleep in cudaStreamSynchronize instead of spinning (hosts with fewer
+    // cores than threads waiting on the GPU); must be set before the context exists, ignored afterwards
+    if (getenv("KID_SYNC_BLOCKING")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
     e = cudaFree(nullptr); // forces the primary context into existence
     if (e != cudaSuccess) return fail(KID_ECUDA, "kid_device_init: %s", cudaGetErrorString(e));
     __atomic_store_n(&g_host_alloc_device, device, __ATOMIC_RELAXED);

@@ -835,8 +835,17 @@ struct GzLoader {
         uint64_t done = 0;
         int which = 0;
         bool used[2] = { false, false };
+        const bool timing = getenv("KID_GZ_GPU_TIMING") != nullptr;
+        double t_wait = 0, t_read = 0, t_copy = 0, t_mark = timing ? now_s() : 0;
+        auto lap = [&](double &acc) {
+            if (!timing) return;
+            const double t = now_s();
+            acc += t - t_mark;
+            t_mark = t;
+        };
         while (done < size) {
             if (used[which]) KID_CUDA(cudaEventSynchronize(ev[which]));
+            lap(t_wait);
             uint8_t *dst = stage[which].as<uint8_t>();
             size_t got = 0;
             const size_t want = (size_t)std::min<uint64_t>(chunk, size - done);
@@ -845,6 +854,7 @@ struct GzLoader {
                 if (r <= 0) { why = "read error"; return KID_EUNSUPPORTED; }
                 got += (size_t)r;
             }
+            lap(t_read);
             if (done == 0) {
                 const uint64_t hl = gzip_header_len(dst, std::min<uint64_t>(size, want), 0);
                 if (!hl) { why = "no gzip header"; return KID_EUNSUPPORTED; }
@@ -861,8 +871,11 @@ struct GzLoader {
             used[which] = true;
             which ^= 1;
             done += want;
+            lap(t_copy);
         }
         KID_CUDA(cudaStreamSynchronize(stream));
+        lap(t_wait);
+        if (timing) fprintf(stderr, "[kid_fastq] %s: pread %.3f s, copy calls %.3f s, waiting for copies %.3f s\n", path, t_read, t_copy, t_wait);
         return KID_OK;
     }
     void release()
@@ -985,9 +998,13 @@ int kid_fastq_prefetch_gz_file(kid_fastq *f, const char *path)
     f->pre_active = true;
     GzLoader *ld = &f->loader[1 - f->cur];
     const int device = f->db->device;
-    f->pre_thread = std::thread([f, ld, device] {
+    const double t_call = now_s();
+    f->pre_thread = std::thread([f, ld, device, t_call] {
         cudaSetDevice(device);
+        const double t_go = now_s();
         f->pre_rc = ld->read(f->pre_path.c_str());
+        if (getenv("KID_GZ_GPU_TIMING"))
+            fprintf(stderr, "[kid_fastq] %s: read ahead, thread up after %.3f s, done after %.3f s\n", f->pre_path.c_str(), t_go - t_call, now_s() - t_call);
     });
     return KID_OK;
 }
@@ -1008,6 +1025,7 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     GzLoader *ld = nullptr;
     if (f->pre_active) {
         f->pre_thread.join();
+        if (getenv("KID_GZ_GPU_TIMING")) fprintf(stderr, "[kid_fastq] %s: waited %.3f s for the read-ahead\n", path, now_s() - t0);
         f->pre_active = false;
         if (f->pre_path == path) {
             ld = &f->loader[1 - f->cur];
@@ -1030,7 +1048,9 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     const uint32_t slot = (uint32_t)slot64;
     {
         size_t free_b = 0, total_b = 0;
+        const double tq = now_s();
         KID_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (getenv("KID_GZ_GPU_TIMING")) fprintf(stderr, "[kid_fastq] %s: cudaMemGetInfo %.3f s\n", path, now_s() - tq);
         // symbols (2 bytes each, reserved per piece), then text, maps, batch and packed words: ~4x the text
         const uint64_t need = (uint64_t)n_pieces * slot * 2 + size * f->expand * 5 + (uint64_t)n_pieces * kWin * 2;
         const uint64_t have = free_b + f->syms.cap + f->pm.cap + f->text.cap + f->seq.cap + f->qual.cap + f->words.cap;

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
+#include <future>
 #include <condition_variable>
 #include <iostream>
 #include <map>
@@ -76,6 +77,11 @@ struct GpuReader {
     kid_fastq *fq = nullptr;
     int32_t *taxon = nullptr; // page-locked
     size_t cap = 0;
+    // the same file of the NEXT sample, being read, inflated and framed by a helper thread while this
+    // thread still assembles and writes what the current one produced
+    std::future<int> ahead;
+    std::string ahead_path, ahead_error;
+    size_t ahead_reads = 0;
 };
 
 GpuReader &gpu_reader(kid_sample *smp, int which)
@@ -97,13 +103,24 @@ bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std
     GpuReader &gr = gpu_reader(smp, which);
     const double t_begin = now();
     size_t n = 0;
-    const int rc = kid_fastq_load_gz_file(gr.fq, path.c_str(), &n);
+    int rc;
+    std::string error;
+    if (gr.ahead.valid() && gr.ahead_path == path) {
+        rc = gr.ahead.get();
+        n = gr.ahead_reads;
+        error = gr.ahead_error;
+    } else {
+        if (gr.ahead.valid()) gr.ahead.get(); // some other file: that work is lost
+        rc = kid_fastq_load_gz_file(gr.fq, path.c_str(), &n);
+        if (rc != 0) error = kid_last_error();
+    }
     if (rc == KID_EUNSUPPORTED) {
-        if (stats) fprintf(stderr, "[nk10] %s\n", kid_last_error());
+        if (stats) fprintf(stderr, "[nk10] %s\n", error.c_str());
         return false;
     }
-    if (rc != 0) die(1, kid_last_error());
-    // the same file of the next sample is read (and copied to the device) while this one is classified and written
+    if (rc != 0) die(1, error);
+    // the next sample's file: its bytes are read and copied to the device from now on (a second buffer), its
+    // kernels start once this file's reads have been fetched (below)
     if (!next_path.empty() && kid_fastq_prefetch_gz_file(gr.fq, next_path.c_str()) != 0) die(1, kid_last_error());
     if (n > gr.cap) {
         kid_host_free(gr.taxon);
@@ -128,6 +145,22 @@ bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std
     const char *data = nullptr;
     const uint32_t *lens = nullptr;
     if (kid_fastq_fetch(gr.fq, pick.data(), pick.size(), &data, &lens) != 0) die(1, kid_last_error());
+    uint64_t st_text = 0, st_pieces = 0, st_again = 0, st_members = 0;
+    double ph[8] = { 0 };
+    if (stats) kid_fastq_stats(gr.fq, &st_text, &st_pieces, &st_again, &st_members, ph, 8);
+    const double t_fetched = now();
+    // Everything this file still needs is on the host now (data / lens stay valid until the next fetch, the
+    // taxa are in gr.taxon): the next sample's file may take the device buffers.  Loading touches no
+    // kid_sample, so it can run under the rest of this sample.
+    if (!next_path.empty()) {
+        gr.ahead_path = next_path;
+        GpuReader *g = &gr;
+        gr.ahead = std::async(std::launch::async, [g] {
+            const int r = kid_fastq_load_gz_file(g->fq, g->ahead_path.c_str(), &g->ahead_reads);
+            g->ahead_error = r != 0 ? kid_last_error() : "";
+            return r;
+        });
+    }
     // ">taxon:header\nbases\n" per read (the bytes of :610), assembled in one buffer
     size_t at = 0, total = 0;
     for (size_t i = 0; i < pick.size(); i++) total += lens[2 * i] + lens[2 * i + 1] + 16;
@@ -159,15 +192,12 @@ bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std
     if (outread) outread->write(text.data(), (std::streamsize)text.size());
     if (outread) outread->flush();
     if (stats) {
-        fprintf(stderr, "[nk10] %s: load %.3f classify %.3f pick+fetch+write %.3f s (%zu reads written)\n", path.c_str(), t_loaded - t_begin,
-                t_classified - t_loaded, now() - t_classified, pick.size());
-        uint64_t text = 0, pieces = 0, again = 0, members = 0;
-        double ph[8] = { 0 };
-        kid_fastq_stats(gr.fq, &text, &pieces, &again, &members, ph, 8);
+        fprintf(stderr, "[nk10] %s: load (or the wait for it) %.3f classify %.3f pick+fetch %.3f write %.3f s (%zu reads written)\n",
+                path.c_str(), t_loaded - t_begin, t_classified - t_loaded, t_fetched - t_classified, now() - t_fetched, pick.size());
         fprintf(stderr, "[nk10] %s on the device: %zu reads, %llu bytes of text in %llu pieces (%llu inflated again), %llu members; "
                         "read %.3f find %.3f inflate %.3f chain %.3f resolve %.3f frame %.3f classify %.3f fetch %.3f s\n",
-                path.c_str(), n, (unsigned long long)text, (unsigned long long)pieces, (unsigned long long)again,
-                (unsigned long long)members, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+                path.c_str(), n, (unsigned long long)st_text, (unsigned long long)st_pieces, (unsigned long long)st_again,
+                (unsigned long long)st_members, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
     }
     return true;
 }

@@ -1,11 +1,12 @@
 #!/bin/bash
-# round-2 GPU check R: hosts after the warm-up change (drop-in tests, file-level timing)
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_nk10_dropin.py tests/test_kmerread_dropin.py tests/test_kmerreadc_dropin.py tests/test_golden_ref_case.py -m gpu -x -q > gpurun_out/gputests_r.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gputests_r.log
-tail -n 3 gpurun_out/gputests_r.log
-timeout 600 python bench.py --no-e2e --no-cpu-baseline --steps 3 > gpurun_out/bench_r.json 2> gpurun_out/bench_r.err
-python - <<'P'
-import json
-d=json.loads(open("gpurun_out/bench_r.json").read().strip().splitlines()[-1])
-print(d["files_e2e"])
-P
+# where the read phase of the device reader spends its time when files are loaded ahead
+R=$GRAFT_REPO_ROOT
+W=/tmp/kid_v; mkdir -p $W; cd $W
+nproc; free -g | head -2; cat /sys/fs/cgroup/cpu.max 2>/dev/null
+$R/tools/kid_synth db --golden $R/tests/golden/b10 --out $W --den 100 > /dev/null
+for i in 0 1 2 3 4; do $R/tools/kid_synth reads --golden $R/tests/golden/b10 --out $W/fq --sample s$i --pairs 2000000 --first-pair $((i*2000000)) --den 100 > /dev/null; done
+KID_STATS=1 KID_GPUS=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ 2>&1 >/dev/null | grep "reads,"
+echo "== timing"
+KID_STATS=1 KID_GPUS=1 KID_GZ_GPU_TIMING=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ 2>&1 >/dev/null | grep "reads,\|kid_fastq" | sed -e 's#/tmp/kid_v/fq/##'
+exit 0
+KID_SYNC_BLOCKING=1 KID_STATS=1 KID_GPUS=1 KID_GZ_GPU_TIMING=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ 2>&1 >/dev/null | grep "reads,\|kid_fastq" | sed -e 's#/tmp/kid_v/fq/##'

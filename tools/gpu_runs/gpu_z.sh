@@ -18,9 +18,6 @@ done
 echo "== untimed"
 KID_STATS=1 KID_GPUS=1 timeout 300 $R/kmer_id_b200/bin/nk10 $W/fq/ 2>&1 >/dev/null | grep "reads,\|total"
 cp $W/gpu.err $R/gpurun_out/z_gpu.err
-cd $R
-timeout 600 python -m pytest tests/test_gpu_ingest.py tests/test_nk10_dropin.py -m gpu -q --tb=short -x > gpurun_out/gputests_z.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gputests_z.log
-tail -n 4 gpurun_out/gputests_z.log
-# per-kernel times of one nk10 run on one sample (serialised by ncu: shares, not absolutes)
 cd $W; rm -f $W/fq/s1_* $W/fq/s2_* $W/fq/s3_* $W/fq/s4_*
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $R/gpurun_out/z_launches.csv env KID_GPUS=1 $R/kmer_id_b200/bin/nk10 $W/fq/ > /dev/null 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kidz_\(inflate_kernel\|find\|copy\) -c 3 -f -o $R/gpurun_out/prof_r2_ingest env KID_GPUS=1 KID_SERIAL=1 $R/kmer_id_b200/bin/nk10 $W/fq/ > $R/gpurun_out/ncu_z.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $R/gpurun_out/z_launches.csv env KID_GPUS=1 KID_SERIAL=1 $R/kmer_id_b200/bin/nk10 $W/fq/ > /dev/null 2>&1; echo "ncu rc=$?"
