@@ -7,8 +7,8 @@
 // libkmerid_b200.so (include/kmer_id.h); there is no CPU classification path in this program.
 //
 // Extras that do not change the contract: all visible GPUs are used (KID_GPUS=<k> limits them,
-// KID_DEVICE=<n> pins one; whole samples are dealt to the GPUs when there are several, a single sample is
-// split over all of them: KID_MULTI_MODE=samples|reads forces either), gz FASTQ files are inflated and
+// KID_DEVICE=<n> pins one; KID_MULTI_MODE=samples deals whole samples to the GPUs instead of splitting
+// every sample over them), gz FASTQ files are inflated and
 // framed on the GPU (KID_GPU_INGEST=0: on the host), KID_STATS=1 prints phase
 // timings to stderr, and the parsed probe list is cached next to probes10.txt.gz as
 // probes10.txt.gz.kidcache (stamped with the text file's size and mtime; KID_NO_CACHE=1 disables it).
@@ -355,11 +355,11 @@ int main(int argc, char *argv[])
     // KID_SERIAL=1 processes R1 then R2 on one thread, like the reference.
     const bool serial = getenv("KID_SERIAL") != nullptr;
     const int n_gpus = (int)gpus.devices.size();
-    // several GPUs: whole samples are dealt to the GPUs when there are several samples (no exchange at all, and
-    // with the device-side reader every GPU inflates its own files); a lone sample is split over all GPUs.
-    // KID_MULTI_MODE=samples / reads forces one or the other.
+    // several GPUs: every sample is split over the GPUs (with the device-side reader: R1 on the first, R2 on the
+    // second, one exchange at sample end); KID_MULTI_MODE=samples deals whole samples to the GPUs instead (no
+    // exchange; GPU g takes samples g, g + n, ...), which is what pays with many samples and more than 2 GPUs
     const char *mm = getenv("KID_MULTI_MODE");
-    const bool by_sample = n_gpus > 1 && (mm ? std::string(mm) == "samples" : fnames.size() > 1);
+    const bool by_sample = n_gpus > 1 && mm && std::string(mm) == "samples";
     if (!by_sample) {
         // every sample on all GPUs: its batches are dealt to the GPUs, one exchange at sample end
         for (size_t i = 0; i < fnames.size(); i++) {
@@ -375,21 +375,17 @@ int main(int argc, char *argv[])
         std::vector<char> finished(fnames.size(), 0);
         std::mutex mu;
         std::condition_variable cv;
-        size_t next_sample = 0, next_print = 0;
+        size_t next_print = 0;
         std::vector<std::thread> th;
         for (int g = 0; g < n_gpus; g++)
             th.emplace_back([&, g] {
                 kid_sample *smp = gpus.samples[(size_t)g];
-                for (;;) {
-                    size_t i;
-                    {
-                        std::lock_guard<std::mutex> lk(mu);
-                        if (next_sample >= fnames.size()) return;
-                        i = next_sample++;
-                    }
+                // a fixed deal, so that every GPU knows its next sample and reads it ahead
+                for (size_t i = (size_t)g; i < fnames.size(); i += (size_t)n_gpus) {
                     if (kid_sample_begin(smp, nullptr) != 0) die(1, kid_last_error());
                     std::ostringstream log;
-                    process_sample(&smp, 1, dname, fnames[i], std::string(), serial, (unsigned)n_gpus, log,
+                    const std::string next = i + (size_t)n_gpus < fnames.size() ? fnames[i + (size_t)n_gpus] : std::string();
+                    process_sample(&smp, 1, dname, fnames[i], next, serial, (unsigned)n_gpus, log,
                                    [&](int32_t *gc, int32_t *uc) { if (kid_sample_counts(smp, gc, uc, nullptr) != 0) die(1, kid_last_error()); },
                                    stats, nullptr);
                     {
