@@ -72,6 +72,41 @@ __device__ __forceinline__ uint32_t queue_drop32(uint32_t *q, uint32_t qn, uint3
     return qn - nb;
 }
 
+// Stages two and three over the queues; `more` = the piece has positions left (then the queues only have
+// to get below 32 entries), else everything is drained.  Returns the piece-relative bit of the first
+// position that passes the full test, or kNoBit.  Kept out of line: inlined, its header parser pushed the
+// scan loop's own variables into local memory (90 instructions per 32 positions instead of 25).
+constexpr uint32_t kNoBit = 0xFFFFFFFFu;
+struct FindQueues {
+    uint32_t found, n1, n2;
+};
+__device__ __noinline__ FindQueues find_drain(const uint32_t *w, const uint32_t *wp, uint64_t from, uint32_t *q1, uint32_t *q2, uint16_t *tabmem,
+                                              uint32_t n1, uint32_t n2, bool more, bool text_only, uint32_t lane)
+{
+    Tab<32> tab{ tabmem + lane };
+    uint32_t found = kNoBit;
+    for (;;) {
+        while ((n1 >= 32 || (!more && n1 > 0)) && n2 < 32) {
+            const uint32_t c = lane < n1 ? q1[lane] : 0u;
+            const bool pass = lane < n1 && block_start_cl_complete(wp, c, peek32(wp, c));
+            n2 = queue_push(q2, n2, pass, c, lane); // <= 63
+            n1 = queue_drop32(q1, n1, lane);
+        }
+        while (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
+            const uint32_t c = lane < n2 ? q2[lane] : 0u;
+            const bool ok = lane < min(n2, 32u) && is_block_start(w, from + c, tab, text_only);
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (m) {
+                found = __shfl_sync(kFull, c, __ffs(m) - 1);
+                break;
+            }
+            n2 = queue_drop32(q2, n2, lane);
+        }
+        if (found != kNoBit || !(n1 >= 32 || (!more && n1 > 0))) break;
+    }
+    return FindQueues{ found, n1, n2 };
+}
+
 __global__ void __launch_bounds__(kFindWarps * 32)
 kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_t n_pieces, bool text_only, uint64_t *start_bit)
 {
@@ -80,50 +115,33 @@ kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_
     const uint32_t k = 1u + blockIdx.x * kFindWarps + warp;
     if (k >= n_pieces) return;
     uint16_t *wmem = smem + warp * kFindWarpEntries;
-    Tab<32> tab{ wmem + lane };
     uint32_t *q1 = reinterpret_cast<uint32_t *>(wmem + 32 * kFindTabEntries), *q2 = q1 + 64;
     const uint64_t from = (uint64_t)k * piece_bytes * 8; // a multiple of 32: piece_bytes is one of 4
     const uint32_t *wp = w + (from >> 5);
     const uint32_t n_bits = (uint32_t)(min(size, ((uint64_t)k + 1) * piece_bytes) * 8 - from);
-    uint32_t n1 = 0, n2 = 0;
-    uint64_t found = ~0ull;
+    const uint32_t n_iter = (n_bits + 31u) >> 5;
+    uint32_t n1 = 0, n2 = 0, found = kNoBit;
     uint32_t mine = 0, after = 0; // 32 words of the piece, one per lane, and the word behind them
-    for (uint32_t it = 0; found == ~0ull; it++) { // positions 32 it .. 32 it + 31, one per lane
-        const bool more = it * 32u < n_bits;
-        if (more) {
-            if ((it & 31u) == 0) {
-                mine = wp[it + lane];
-                after = wp[it + 32u];
-            }
-            const uint32_t lo = __shfl_sync(kFull, mine, (int)(it & 31u));
-            const uint32_t nx = __shfl_sync(kFull, mine, (int)((it + 1u) & 31u));
-            const uint32_t v = __funnelshift_r(lo, (it & 31u) == 31u ? after : nx, lane);
-            const uint32_t r = it * 32u + lane;
-            n1 = queue_push(q1, n1, r < n_bits && block_start_bits_plausible(v), r, lane);
+    for (uint32_t it = 0; it < n_iter; it++) { // positions 32 it .. 32 it + 31, one per lane
+        if ((it & 31u) == 0) {
+            mine = wp[it + lane];
+            after = wp[it + 32u];
         }
-        if (n1 < 32 && more) continue;
-        for (;;) { // drain: q1 below 32 entries (empty at the end of the piece), q2 likewise
-            while ((n1 >= 32 || (!more && n1 > 0)) && n2 < 32) {
-                const uint32_t c = lane < n1 ? q1[lane] : 0u;
-                const bool pass = lane < n1 && block_start_cl_complete(wp, c, peek32(wp, c));
-                n2 = queue_push(q2, n2, pass, c, lane); // <= 63
-                n1 = queue_drop32(q1, n1, lane);
-            }
-            while (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
-                const uint32_t c = lane < n2 ? q2[lane] : 0u;
-                const bool ok = lane < min(n2, 32u) && is_block_start(w, from + c, tab, text_only);
-                const unsigned m = __ballot_sync(kFull, ok);
-                if (m) {
-                    found = from + __shfl_sync(kFull, c, __ffs(m) - 1);
-                    break;
-                }
-                n2 = queue_drop32(q2, n2, lane);
-            }
-            if (found != ~0ull || !(n1 >= 32 || (!more && n1 > 0))) break;
+        const uint32_t lo = __shfl_sync(kFull, mine, (int)(it & 31u));
+        const uint32_t nx = __shfl_sync(kFull, mine, (int)((it + 1u) & 31u));
+        const uint32_t v = __funnelshift_r(lo, (it & 31u) == 31u ? after : nx, lane);
+        const uint32_t r = it * 32u + lane;
+        n1 = queue_push(q1, n1, r < n_bits && block_start_bits_plausible(v), r, lane);
+        if (n1 >= 32) {
+            const FindQueues q = find_drain(w, wp, from, q1, q2, wmem, n1, n2, true, text_only, lane);
+            n1 = q.n1;
+            n2 = q.n2;
+            found = q.found;
+            if (found != kNoBit) break;
         }
-        if (!more && n1 == 0 && n2 == 0) break;
     }
-    if (lane == 0) start_bit[k] = found;
+    if (found == kNoBit) found = find_drain(w, wp, from, q1, q2, wmem, n1, n2, false, text_only, lane).found;
+    if (lane == 0) start_bit[k] = found == kNoBit ? ~0ull : from + found;
 }
 
 // ------------------------------------------------------------------------------------- inflate
@@ -321,6 +339,26 @@ kidz_inflate_one_kernel(const InflateArgs a, uint32_t k, uint64_t start)
 // lies before the chunk is one gather load (everything before the chunk is final), one whose source lies
 // inside the chunk is chased through the lanes with shuffles (pointer jumping, <= 5 rounds).  The codes of
 // the next chunk are loaded before this chunk's gather comes back.
+// chase of the copies whose source lies inside the same chunk of 32 positions: sl = source lane (below
+// the lane's own), done = the lane holds its final symbol
+__device__ __forceinline__ uint32_t chase_in_chunk(uint32_t v, uint32_t sl, bool done)
+{
+    unsigned pending = __ballot_sync(kFull, !done);
+    while (pending) {
+        const uint32_t vv = __shfl_sync(kFull, v, (int)sl);
+        const int dd = __shfl_sync(kFull, (int)done, (int)sl);
+        const uint32_t ss = __shfl_sync(kFull, sl, (int)sl);
+        if (!done) {
+            if (dd) {
+                v = vv;
+                done = true;
+            } else sl = ss;
+        }
+        pending = __ballot_sync(kFull, !done);
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(64)
 kidz_copy_kernel(uint16_t *syms, uint32_t slot, const PieceResult *res, uint32_t k0, uint32_t n_pieces)
 {
@@ -329,37 +367,44 @@ kidz_copy_kernel(uint16_t *syms, uint32_t slot, const PieceResult *res, uint32_t
     if (k >= n_pieces || res[k].status != kPieceOk) return;
     const uint32_t n = res[k].n_out;
     uint16_t *out = syms + (size_t)k * slot;
-    uint32_t x_next = lane < n ? out[lane] : 0u;
-    for (uint32_t p = 0; p < n; p += 32) {
-        const uint32_t x = x_next;
-        if (p + 32u + lane < n) x_next = out[p + 32u + lane];
-        const bool have = p + lane < n;
-        uint32_t v = x, sl = lane;
-        bool done = true;
-        if (have && (x & kCopyFlag)) {
-            const int32_t src = (int32_t)(p + lane) - (int32_t)((x & 0x7fffu) + 1u);
-            if (src < 0) v = (uint32_t)(256 + kWin + src);
-            else if ((uint32_t)src < p) v = __ldcg(out + src);
+    // two chunks (A: p.., B: p + 32..) per round, so that two gathers per lane are in flight; the codes of the
+    // next round are loaded before this round's gathers come back
+    uint32_t a_next = lane < n ? out[lane] : 0u, b_next = 32u + lane < n ? out[32u + lane] : 0u;
+    for (uint32_t p = 0; p < n; p += 64) {
+        const uint32_t xa = a_next, xb = b_next;
+        if (p + 64u + lane < n) a_next = out[p + 64u + lane];
+        if (p + 96u + lane < n) b_next = out[p + 96u + lane];
+        const bool have_a = p + lane < n, have_b = p + 32u + lane < n;
+        uint32_t va = xa, sla = lane, vb = xb, slb = lane;
+        bool done_a = true, done_b = true, from_a = false;
+        if (have_a && (xa & kCopyFlag)) {
+            const int32_t src = (int32_t)(p + lane) - (int32_t)((xa & 0x7fffu) + 1u);
+            if (src < 0) va = (uint32_t)(256 + kWin + src);
+            else if ((uint32_t)src < p) va = __ldcg(out + src);
             else {
-                done = false;
-                sl = (uint32_t)src - p;
+                done_a = false;
+                sla = (uint32_t)src - p;
             }
         }
-        unsigned pending = __ballot_sync(kFull, !done);
-        while (pending) {
-            const uint32_t vv = __shfl_sync(kFull, v, (int)sl);
-            const int dd = __shfl_sync(kFull, (int)done, (int)sl);
-            const uint32_t ss = __shfl_sync(kFull, sl, (int)sl);
-            if (!done) {
-                if (dd) {
-                    v = vv;
-                    done = true;
-                } else sl = ss;
+        if (have_b && (xb & kCopyFlag)) {
+            const int32_t src = (int32_t)(p + 32u + lane) - (int32_t)((xb & 0x7fffu) + 1u);
+            if (src < 0) vb = (uint32_t)(256 + kWin + src);
+            else if ((uint32_t)src < p) vb = __ldcg(out + src);
+            else if ((uint32_t)src < p + 32u) { // in chunk A: after A is final
+                from_a = true;
+                slb = (uint32_t)src - p;
+            } else {
+                done_b = false;
+                slb = (uint32_t)src - p - 32u;
             }
-            pending = __ballot_sync(kFull, !done);
         }
-        if (have) out[p + lane] = (uint16_t)v;
-        __syncwarp(); // the next chunk's gathers may read these
+        va = chase_in_chunk(va, sla, done_a);
+        const uint32_t fa = __shfl_sync(kFull, va, (int)(from_a ? slb : lane));
+        if (from_a) vb = fa;
+        vb = chase_in_chunk(vb, slb, done_b);
+        if (have_a) out[p + lane] = (uint16_t)va;
+        if (have_b) out[p + 32u + lane] = (uint16_t)vb;
+        __syncwarp(); // the next round's gathers may read these
     }
 }
 
