@@ -43,8 +43,9 @@ using namespace kidz;
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kFindWarps = 4;
-constexpr int kFindWarpEntries = 32 * kFindTabEntries + 256; // + two queues of 64 candidate offsets
+constexpr int kFindWarps = 8;
+constexpr int kFindLanes = 8; // lanes of a warp that run the full header parse at a time (each needs its own tables)
+constexpr int kFindWarpEntries = kFindLanes * kFindTabEntries + 256; // + two queues of 64 candidate offsets
 constexpr int kInflateWarps = 4;
 constexpr uint32_t kRefLineLimit = 0x4000;                  // BUFLEN, newkmer_10nx.cpp:85
 constexpr uint32_t kErrLongLine = 1u, kErrShortQual = 2u;
@@ -83,7 +84,7 @@ struct FindQueues {
 __device__ __noinline__ FindQueues find_drain(const uint32_t *w, const uint32_t *wp, uint64_t from, uint32_t *q1, uint32_t *q2, uint16_t *tabmem,
                                               uint32_t n1, uint32_t n2, bool more, bool text_only, uint32_t lane)
 {
-    Tab<32> tab{ tabmem + lane };
+    Tab<kFindLanes> tab{ tabmem + (lane % kFindLanes) };
     uint32_t found = kNoBit;
     for (;;) {
         while ((n1 >= 32 || (!more && n1 > 0)) && n2 < 32) {
@@ -93,13 +94,16 @@ __device__ __noinline__ FindQueues find_drain(const uint32_t *w, const uint32_t 
             n1 = queue_drop32(q1, n1, lane);
         }
         while (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
-            const uint32_t c = lane < n2 ? q2[lane] : 0u;
-            const bool ok = lane < min(n2, 32u) && is_block_start(w, from + c, tab, text_only);
-            const unsigned m = __ballot_sync(kFull, ok);
-            if (m) {
-                found = __shfl_sync(kFull, c, __ffs(m) - 1);
-                break;
+            const uint32_t nb = min(n2, 32u);
+            for (uint32_t c0 = 0; c0 < nb && found == kNoBit; c0 += kFindLanes) { // rare: kFindLanes candidates at a time
+                const uint32_t i = c0 + lane;
+                const uint32_t c = lane < kFindLanes && i < nb ? q2[i] : 0u;
+                const bool ok = lane < kFindLanes && i < nb && is_block_start(w, from + c, tab, text_only);
+                const unsigned m = __ballot_sync(kFull, ok);
+                if (m) found = __shfl_sync(kFull, c, __ffs(m) - 1);
+                __syncwarp();
             }
+            if (found != kNoBit) break;
             n2 = queue_drop32(q2, n2, lane);
         }
         if (found != kNoBit || !(n1 >= 32 || (!more && n1 > 0))) break;
@@ -115,7 +119,7 @@ kidz_find_kernel(const uint32_t *w, uint64_t size, uint64_t piece_bytes, uint32_
     const uint32_t k = 1u + blockIdx.x * kFindWarps + warp;
     if (k >= n_pieces) return;
     uint16_t *wmem = smem + warp * kFindWarpEntries;
-    uint32_t *q1 = reinterpret_cast<uint32_t *>(wmem + 32 * kFindTabEntries), *q2 = q1 + 64;
+    uint32_t *q1 = reinterpret_cast<uint32_t *>(wmem + kFindLanes * kFindTabEntries), *q2 = q1 + 64;
     const uint64_t from = (uint64_t)k * piece_bytes * 8; // a multiple of 32: piece_bytes is one of 4
     const uint32_t *wp = w + (from >> 5);
     const uint32_t n_bits = (uint32_t)(min(size, ((uint64_t)k + 1) * piece_bytes) * 8 - from);
