@@ -94,6 +94,59 @@ GpuReader &gpu_reader(kid_sample *smp, int which)
     return r;
 }
 
+// process_read's bookkeeping (:608-614) replayed over a whole file's taxa: which reads go to _reads.txt (fewer than
+// SAVENUM reads of their taxon came before them, in file order), gcount and tct.  Order dependent, so on several
+// threads it takes two passes: per-chunk taxon counts, then every chunk starts from the counts before it.
+void pick_reads(const int32_t *taxon, size_t n, SampleState &st, std::vector<uint32_t> &pick)
+{
+    const size_t n_taxa = st.gcount_host.size();
+    const unsigned T = n >= ((size_t)1 << 18) ? 4u : 1u;
+    std::vector<std::vector<int>> count(T, std::vector<int>(n_taxa, 0));
+    std::vector<std::vector<uint32_t>> picks(T);
+    std::vector<long long> kept(T, 0);
+    auto chunk = [&](unsigned c) { return n * c / T; };
+    auto on_chunks = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (unsigned c = 1; c < T; c++) th.emplace_back(fn, c);
+        fn(0u);
+        for (auto &t : th) t.join();
+    };
+    on_chunks([&](unsigned c) { // reads per taxon in this chunk
+        std::vector<int> &h = count[c];
+        long long k = 0;
+        for (size_t r = chunk(c); r < chunk(c + 1); r++) {
+            const int fin = taxon[r];
+            if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
+            h[(size_t)fin]++;
+            k++;
+        }
+        kept[c] = k;
+    });
+    for (size_t t = 0; t < n_taxa; t++) { // count[c][t] := reads of taxon t before chunk c
+        int before = st.gcount_host[t];
+        for (unsigned c = 0; c < T; c++) {
+            const int here = count[c][t];
+            count[c][t] = before;
+            before += here;
+        }
+        st.gcount_host[t] = before;
+    }
+    on_chunks([&](unsigned c) {
+        std::vector<int> &h = count[c];
+        std::vector<uint32_t> &out = picks[c];
+        for (size_t r = chunk(c); r < chunk(c + 1); r++) {
+            const int fin = taxon[r];
+            if (fin < 0) continue;
+            if (fin > 1 && h[(size_t)fin] < SAVENUM) out.push_back((uint32_t)r);
+            h[(size_t)fin]++;
+        }
+    });
+    for (unsigned c = 0; c < T; c++) {
+        pick.insert(pick.end(), picks[c].begin(), picks[c].end());
+        st.tct += kept[c];
+    }
+}
+
 // false: the file is one for the host reader (nothing has been counted)
 bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std::string &next_path, SampleState &st,
                   std::ostream *outread, std::vector<SavedRead> *saved, bool stats)
@@ -135,13 +188,7 @@ bool run_file_gpu(kid_sample *smp, int which, const std::string &path, const std
     const double t_classified = now();
     // the reads process_read would write (:608-611): fewer than SAVENUM of their taxon came before them
     std::vector<uint32_t> pick;
-    for (size_t r = 0; r < n; r++) {
-        const int fin = gr.taxon[r];
-        if (fin < 0) continue; // trimmed below 31 bases: the read vanishes (:755)
-        if (fin > 1 && st.gcount_host[(size_t)fin] < SAVENUM) pick.push_back((uint32_t)r);
-        st.gcount_host[(size_t)fin]++;
-        st.tct++;
-    }
+    pick_reads(gr.taxon, n, st, pick);
     const char *data = nullptr;
     const uint32_t *lens = nullptr;
     if (kid_fastq_fetch(gr.fq, pick.data(), pick.size(), &data, &lens) != 0) die(1, kid_last_error());
