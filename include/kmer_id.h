@@ -303,8 +303,9 @@ int kid_ucount_range_device(const kid_db *db, const uint32_t *seen, uint64_t wor
  *                           KID_EUNSUPPORTED: a file this path does not reproduce byte for byte (no gzip
  *                           header, fixed/stored-only deflate streams, trailing bytes or a bad CRC-32 /
  *                           ISIZE - zlib has to judge those -, a line of >= 16 KiB (fatal at :773), a
- *                           quality line shorter than its read (the reference aborts at :729), more than
- *                           4 GiB of text or than device memory holds).  Nothing has been counted: read
+ *                           quality line shorter than its read (the reference aborts at :729), more text
+ *                           than device memory holds: the whole file is inflated at once, ~45 bytes of
+ *                           device memory per compressed byte).  Nothing has been counted: read
  *                           the file with the host reader, whose error behaviour is the reference's.
  *   kid_fastq_prefetch_gz_file  optional: starts reading `path` into a second device buffer on a helper thread
  *                           and returns at once; a later kid_fastq_load_gz_file of the same path finds the

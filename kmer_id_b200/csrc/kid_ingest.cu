@@ -13,8 +13,8 @@
 //
 // Anything this path does not reproduce byte for byte - a file zlib has to judge (no gzip header,
 // trailing bytes, a bad check value, fixed/stored-only streams), a line of >= 16 KiB (fatal in the
-// reference), a quality line shorter than its read (the reference aborts), more text than 4 GiB or than
-// device memory holds - makes kid_fastq_load_gz_file return KID_EUNSUPPORTED BEFORE anything was
+// reference), a quality line shorter than its read (the reference aborts), more text than device memory
+// holds (the whole file is inflated at once) - makes kid_fastq_load_gz_file return KID_EUNSUPPORTED BEFORE anything was
 // counted; the caller then reads the file with the host reader, whose error behaviour is the reference's.
 #include "kid_internal.cuh"
 #include "kid_inflate_chain.hpp"
@@ -564,11 +564,34 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
     return before + incl - v;
 }
 
+// the same over 64-bit values (the spine of the scans: sums of block sums pass 2^32 with more than 4 G bases)
+__device__ __forceinline__ uint64_t block_exclusive_scan64(uint64_t v, uint64_t *warp_sums, uint64_t &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint64_t before = 0, all = 0;
+    for (int i = 0; i < n_warps; i++) {
+        const uint64_t t = warp_sums[i];
+        if (i < warp) before += t;
+        all += t;
+    }
+    total = all;
+    return before + incl - v;
+}
+
 __global__ void __launch_bounds__(1024)
-kidz_scan_sums_kernel(const uint32_t *in, const uint32_t *n_dev, uint32_t n_bound, uint32_t *block_sums)
+kidz_scan_sums_kernel(const uint32_t *in, const uint64_t *n_dev, uint32_t n_bound, uint64_t *block_sums)
 {
     __shared__ uint32_t ws[32];
-    const uint32_t n = n_dev ? min(*n_dev, n_bound) : n_bound;
+    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, (uint64_t)n_bound) : n_bound;
     const uint64_t i0 = ((uint64_t)blockIdx.x * 1024 + threadIdx.x) * 4;
     uint32_t v = 0;
     for (int q = 0; q < 4; q++)
@@ -579,15 +602,15 @@ kidz_scan_sums_kernel(const uint32_t *in, const uint32_t *n_dev, uint32_t n_boun
 }
 
 __global__ void __launch_bounds__(1024)
-kidz_scan_spine_kernel(uint32_t *block_sums, uint32_t n_blocks, uint32_t *total_out)
+kidz_scan_spine_kernel(uint64_t *block_sums, uint32_t n_blocks, uint64_t *total_out)
 {
-    __shared__ uint32_t ws[32];
-    uint32_t carry = 0;
+    __shared__ uint64_t ws[32];
+    uint64_t carry = 0;
     for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
         const uint32_t i = b0 + threadIdx.x;
-        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(v, ws, total);
+        const uint64_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint64_t total;
+        const uint64_t ex = block_exclusive_scan64(v, ws, total);
         if (i < n_blocks) block_sums[i] = carry + ex;
         carry += total;
     }
@@ -596,10 +619,10 @@ kidz_scan_spine_kernel(uint32_t *block_sums, uint32_t n_blocks, uint32_t *total_
 
 template <class OutT>
 __global__ void __launch_bounds__(1024)
-kidz_scan_apply_kernel(const uint32_t *in, const uint32_t *n_dev, uint32_t n_bound, const uint32_t *block_sums, OutT *out)
+kidz_scan_apply_kernel(const uint32_t *in, const uint64_t *n_dev, uint32_t n_bound, const uint64_t *block_sums, OutT *out)
 {
     __shared__ uint32_t ws[32];
-    const uint32_t n = n_dev ? min(*n_dev, n_bound) : n_bound;
+    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, (uint64_t)n_bound) : n_bound;
     const uint64_t i0 = ((uint64_t)blockIdx.x * 1024 + threadIdx.x) * 4;
     uint32_t x[4], v = 0;
     for (int q = 0; q < 4; q++) {
@@ -607,7 +630,7 @@ kidz_scan_apply_kernel(const uint32_t *in, const uint32_t *n_dev, uint32_t n_bou
         v += x[q];
     }
     uint32_t total;
-    uint32_t run = block_sums[blockIdx.x] + block_exclusive_scan(v, ws, total);
+    uint64_t run = block_sums[blockIdx.x] + block_exclusive_scan(v, ws, total);
     for (int q = 0; q < 4; q++) {
         if (i0 + q < n) out[i0 + q] = (OutT)run;
         run += x[q];
@@ -646,7 +669,7 @@ kidz_nl_count_kernel(const uint8_t *text, uint64_t n_text, uint32_t *tile_count)
 }
 
 __global__ void __launch_bounds__(256)
-kidz_nl_write_kernel(const uint8_t *text, uint64_t n_text, const uint32_t *tile_base, uint32_t *nlpos)
+kidz_nl_write_kernel(const uint8_t *text, uint64_t n_text, const uint32_t *tile_base, uint64_t *nlpos)
 {
     __shared__ uint32_t ws[32];
     const uint64_t at = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 16;
@@ -656,37 +679,41 @@ kidz_nl_write_kernel(const uint8_t *text, uint64_t n_text, const uint32_t *tile_
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
-        nlpos[idx++] = (uint32_t)(at + (uint64_t)b);
+        nlpos[idx++] = at + (uint64_t)b;
     }
 }
 
 // line j = text[start, nlpos[j]) with start = nlpos[j-1] + 1; one trailing '\r' does not count (:786-787)
-__device__ __forceinline__ void line_span(const uint8_t *text, const uint32_t *nlpos, uint32_t j, uint32_t &start, uint32_t &len,
-                                          uint32_t *err)
+__device__ __forceinline__ void line_span(const uint8_t *text, const uint64_t *nlpos, uint32_t j, uint64_t &start, uint32_t &len,
+                                          unsigned long long *err)
 {
     start = j ? nlpos[j - 1] + 1u : 0u;
-    const uint32_t e = nlpos[j];
-    len = e - start;
-    if (len >= kRefLineLimit) atomicOr(err, kErrLongLine); // "Buffer to small for input line lengths" (:773)
+    const uint64_t e = nlpos[j];
+    const uint64_t l = e - start;
+    if (l >= kRefLineLimit) atomicOr(err, (unsigned long long)kErrLongLine); // "Buffer to small for input line lengths" (:773)
+    len = (uint32_t)min(l, (uint64_t)kRefLineLimit);
     if (len > 0 && text[e - 1] == '\r') len--;
 }
 
 struct RecordArrays { // one entry per record; positions in the text
-    uint32_t *hdr_start, *hdr_len, *seq_start, *seq_len, *qual_start, *qual_len;
+    uint64_t *hdr_start, *seq_start, *qual_start;
+    uint32_t *hdr_len, *seq_len, *qual_len;
 };
 
 __global__ void __launch_bounds__(256)
-kidz_line_count_kernel(const uint8_t *text, uint64_t n_text, const uint32_t *nlpos, uint32_t n_lines, uint32_t *block_count, uint32_t *err)
+kidz_line_count_kernel(const uint8_t *text, uint64_t n_text, const uint64_t *nlpos, uint32_t n_lines, uint32_t *block_count,
+                       unsigned long long *err)
 {
     __shared__ uint32_t ws[32];
     const uint32_t j = blockIdx.x * 256 + threadIdx.x;
     uint32_t nonempty = 0;
     if (j < n_lines) {
-        uint32_t start, len;
+        uint64_t start;
+        uint32_t len;
         line_span(text, nlpos, j, start, len, err);
         nonempty = len > 0;
         // the unterminated tail of the stream is dropped (:812-813) unless it overflows the line buffer
-        if (j == n_lines - 1 && n_text - ((uint64_t)nlpos[j] + 1) >= kRefLineLimit) atomicOr(err, kErrLongLine);
+        if (j == n_lines - 1 && n_text - (nlpos[j] + 1) >= kRefLineLimit) atomicOr(err, (unsigned long long)kErrLongLine);
     }
     uint32_t total;
     block_exclusive_scan(nonempty, ws, total);
@@ -695,12 +722,13 @@ kidz_line_count_kernel(const uint8_t *text, uint64_t n_text, const uint32_t *nlp
 
 // misc[0] = non-empty lines in total (written by the spine scan); records = that / 4 (:788-802)
 __global__ void __launch_bounds__(256)
-kidz_line_write_kernel(const uint8_t *text, const uint32_t *nlpos, uint32_t n_lines, const uint32_t *block_base, const uint32_t *misc,
-                       RecordArrays rec, uint32_t *err)
+kidz_line_write_kernel(const uint8_t *text, const uint64_t *nlpos, uint32_t n_lines, const uint32_t *block_base, const uint64_t *misc,
+                       RecordArrays rec, unsigned long long *err)
 {
     __shared__ uint32_t ws[32];
     const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-    uint32_t nonempty = 0, start = 0, len = 0;
+    uint32_t nonempty = 0, len = 0;
+    uint64_t start = 0;
     if (j < n_lines) {
         line_span(text, nlpos, j, start, len, err);
         nonempty = len > 0;
@@ -708,7 +736,7 @@ kidz_line_write_kernel(const uint8_t *text, const uint32_t *nlpos, uint32_t n_li
     uint32_t total;
     const uint32_t idx = block_base[blockIdx.x] + block_exclusive_scan(nonempty, ws, total);
     if (!nonempty) return;
-    const uint32_t r = idx >> 2, n_records = misc[0] >> 2;
+    const uint32_t r = idx >> 2, n_records = (uint32_t)(misc[0] >> 2);
     if (r >= n_records) return; // an incomplete last record is never handed to process_qual
     switch (idx & 3u) {
     case 0: rec.hdr_start[r] = start; rec.hdr_len[r] = len; break;
@@ -718,22 +746,22 @@ kidz_line_write_kernel(const uint8_t *text, const uint32_t *nlpos, uint32_t n_li
     }
 }
 
-__global__ void kidz_set_records_kernel(uint32_t *misc)
+__global__ void kidz_set_records_kernel(uint64_t *misc)
 {
     misc[1] = misc[0] >> 2;
 }
 
 // a warp per record: its bases and the qualities under them, appended to the text batch
 __global__ void __launch_bounds__(256)
-kidz_gather_kernel(const uint8_t *text, RecordArrays rec, const uint32_t *misc, const uint64_t *off, uint8_t *seq, uint8_t *qual,
-                   uint32_t *err)
+kidz_gather_kernel(const uint8_t *text, RecordArrays rec, const uint64_t *misc, const uint64_t *off, uint8_t *seq, uint8_t *qual,
+                   unsigned long long *err)
 {
-    const uint32_t n = misc[1];
+    const uint32_t n = (uint32_t)misc[1];
     const int lane = threadIdx.x & 31;
     for (uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
         const uint32_t len = rec.seq_len[r];
         if (rec.qual_len[r] < len) { // qual.at(stop) throws (:729): the reference aborts
-            if (lane == 0) atomicOr(err, kErrShortQual);
+            if (lane == 0) atomicOr(err, (unsigned long long)kErrShortQual);
             continue;
         }
         const uint8_t *s = text + rec.seq_start[r], *q = text + rec.qual_start[r];
@@ -978,11 +1006,11 @@ int set_kernel_attrs(kid_fastq *f)
 
 // exclusive prefix sums of in[0..n) -> out[0..n] on the stream; the total also goes to *total_out (device)
 template <class OutT>
-int scan_u32(kid_fastq *f, const uint32_t *in, const uint32_t *n_dev, uint32_t n_bound, OutT *out, uint32_t *total_out)
+int scan_u32(kid_fastq *f, const uint32_t *in, const uint64_t *n_dev, uint32_t n_bound, OutT *out, uint64_t *total_out)
 {
     const uint32_t nb = (n_bound + 4095) / 4096 + 1; // one block more than needed keeps n_bound == 0 simple
-    KID_CUDA(f->tiles.reserve(sizeof(uint32_t) * ((size_t)nb + 1)));
-    uint32_t *bs = f->tiles.as<uint32_t>();
+    KID_CUDA(f->tiles.reserve(sizeof(uint64_t) * ((size_t)nb + 1)));
+    uint64_t *bs = f->tiles.as<uint64_t>();
     kidz_scan_sums_kernel<<<nb, 1024, 0, f->stream>>>(in, n_dev, n_bound, bs);
     kidz_scan_spine_kernel<<<1, 1024, 0, f->stream>>>(bs, nb, total_out);
     kidz_scan_apply_kernel<OutT><<<nb, 1024, 0, f->stream>>>(in, n_dev, n_bound, bs, out);
@@ -1058,9 +1086,27 @@ int kid_fastq_prefetch_gz_file(kid_fastq *f, const char *path)
     return KID_OK;
 }
 
+static int load_gz_file(kid_fastq *f, const char *path, size_t *n_reads);
+
 int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
 {
     if (!f || !path) return kid_fail(KID_EINVAL, "kid_fastq_load_gz_file: NULL argument");
+    const int rc = load_gz_file(f, path, n_reads);
+    if (rc != KID_ENOMEM) return rc;
+    // an allocation failed after all (another tenant of the GPU, a file that expands more than estimated): the
+    // big buffers go back and the host reader takes the file
+    DeviceGuard guard(f->db->device);
+    cudaStreamSynchronize(f->stream);
+    cudaGetLastError();
+    for (DevBuf *b : { &f->syms, &f->pm, &f->gm, &f->gw, &f->text, &f->nlpos, &f->recs, &f->off, &f->seq, &f->qual, &f->words, &f->meta,
+                       &f->taxon, &f->span })
+        b->release();
+    f->loaded = false;
+    return unsupported(path, "a device allocation failed");
+}
+
+static int load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
+{
     if (n_reads) *n_reads = 0;
     f->loaded = false;
     f->n_reads = 0;
@@ -1100,9 +1146,11 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
         const double tq = now_s();
         KID_CUDA(cudaMemGetInfo(&free_b, &total_b));
         if (getenv("KID_GZ_GPU_TIMING")) fprintf(stderr, "[kid_fastq] %s: cudaMemGetInfo %.3f s\n", path, now_s() - tq);
-        // symbols (2 bytes each, reserved per piece), then text, maps, batch and packed words: ~4x the text
-        const uint64_t need = (uint64_t)n_pieces * slot * 2 + size * f->expand * 5 + (uint64_t)n_pieces * kWin * 2;
-        const uint64_t have = free_b + f->syms.cap + f->pm.cap + f->text.cap + f->seq.cap + f->qual.cap + f->words.cap;
+        // symbols (2 bytes each, reserved per piece) and window maps for sure; text, line and record tables, the text
+        // batch and its packed form (~3.5x the text) for FASTQ's usual 6x expansion - checked again once the text's
+        // size is known
+        const uint64_t need = (uint64_t)n_pieces * slot * 2 + (uint64_t)n_pieces * kWin * 2 + size * 21;
+        const uint64_t have = free_b + f->syms.cap + f->pm.cap + f->text.cap + f->seq.cap + f->qual.cap + f->words.cap + f->nlpos.cap + f->recs.cap;
         if (need + ((uint64_t)2 << 30) > have) return unsupported(path, "not enough device memory for the whole file");
     }
     f->gz_bytes = size;
@@ -1174,7 +1222,15 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     if (cuda_failed) return kid_fail(KID_ECUDA, "kid_fastq_load_gz_file: %s", cudaGetErrorString(cudaGetLastError()));
     if (why) return unsupported(path, why);
     const uint64_t T = chain.text_off.back();
-    if (T >= 0xfff00000ull) return unsupported(path, "more than 4 GiB of text");
+    if (T >= ((uint64_t)1 << 36)) return unsupported(path, "more than 64 GiB of text");
+    {   // what the rest needs on the device, now that the text's size is known: window maps, text, line and record
+        // tables, the text batch, its packed form, per-read results
+        size_t free_b = 0, total_b = 0;
+        KID_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t need = (uint64_t)chain.pieces.size() * kWin * 2 + 3 * T + T / 2;
+        const uint64_t have = free_b + f->pm.cap + f->text.cap + f->seq.cap + f->qual.cap + f->words.cap + f->nlpos.cap + f->recs.cap;
+        if (need + ((uint64_t)1 << 30) > have) return unsupported(path, "not enough device memory for the whole file");
+    }
     f->n_redo = chain.n_redo;
     f->n_covered = chain.n_covered;
     f->n_members = chain.members.size();
@@ -1192,8 +1248,8 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     KID_CUDA(f->gw.reserve((size_t)NG * kWin));
     const size_t text_cap = (size_t)((T + 4095) & ~4095ull) + 4096;
     KID_CUDA(f->text.reserve(text_cap));
-    KID_CUDA(f->misc.reserve(sizeof(uint32_t) * 16));
-    KID_CUDA(f->h_small.reserve(sizeof(uint32_t) * (16 + chain.members.size())));
+    KID_CUDA(f->misc.reserve(sizeof(uint64_t) * 16));
+    KID_CUDA(f->h_small.reserve(sizeof(uint64_t) * 16 + sizeof(uint32_t) * chain.members.size()));
     if (!f->consts_ready) {
         uint32_t c[256 + 32];
         crc_make_table(c);
@@ -1207,7 +1263,7 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     KID_CUDA(cudaMemcpyAsync(f->text_off.p, chain.text_off.data(), sizeof(uint64_t) * ((size_t)M + 1), cudaMemcpyHostToDevice, st));
     KID_CUDA(cudaMemcpyAsync(f->members.p, chain.members.data(), sizeof(Member) * chain.members.size(), cudaMemcpyHostToDevice, st));
     KID_CUDA(cudaMemsetAsync(f->acc.p, 0, sizeof(uint32_t) * chain.members.size(), st));
-    KID_CUDA(cudaMemsetAsync(f->misc.p, 0, sizeof(uint32_t) * 16, st));
+    KID_CUDA(cudaMemsetAsync(f->misc.p, 0, sizeof(uint64_t) * 16, st));
     kidz_maps_kernel<<<NG, 1024, 2 * kWin * 2, st>>>(f->syms.as<uint16_t>(), slot, f->pieces.as<uint32_t>(), f->res.as<PieceResult>(), M, G,
                                                       f->pm.as<uint16_t>(), f->gm.as<uint16_t>());
     kidz_group_windows_kernel<<<1, 1024, 2 * kWin, st>>>(f->gm.as<uint16_t>(), NG, f->gw.as<uint8_t>());
@@ -1223,7 +1279,8 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
         KID_COUNT_LAUNCH();
     }
     // newline counts per 4 KiB tile, their prefix sums in place, the total in misc[2]
-    uint32_t *misc = f->misc.as<uint32_t>();
+    // misc (64-bit words): 0 non-empty lines, 1 records, 2 newlines, 3 error flags, 4 bases
+    uint64_t *misc = f->misc.as<uint64_t>();
     KID_CUDA(f->tilecnt.reserve(sizeof(uint32_t) * ((size_t)n_tiles + 8)));
     uint32_t *tile_cnt = f->tilecnt.as<uint32_t>();
     if (n_tiles) {
@@ -1231,14 +1288,16 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
         KID_COUNT_LAUNCH();
     }
     KID_TRY(scan_u32<uint32_t>(f, tile_cnt, nullptr, n_tiles, tile_cnt, misc + 2));
-    uint32_t *hs = f->h_small.as<uint32_t>();
-    KID_CUDA(cudaMemcpyAsync(hs, misc, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, st));
+    uint64_t *hs = f->h_small.as<uint64_t>();
+    uint32_t *hcrc = reinterpret_cast<uint32_t *>(hs + 16);
+    KID_CUDA(cudaMemcpyAsync(hs, misc, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost, st));
     if (!chain.members.empty())
-        KID_CUDA(cudaMemcpyAsync(hs + 16, f->acc.p, sizeof(uint32_t) * chain.members.size(), cudaMemcpyDeviceToHost, st));
+        KID_CUDA(cudaMemcpyAsync(hcrc, f->acc.p, sizeof(uint32_t) * chain.members.size(), cudaMemcpyDeviceToHost, st));
     KID_CUDA(cudaStreamSynchronize(st));
     for (size_t i = 0; i < chain.members.size(); i++)
-        if (hs[16 + i] != chain.members[i].crc) return unsupported(path, "a member's CRC-32 does not match its trailer");
-    const uint32_t NL = hs[2];
+        if (hcrc[i] != chain.members[i].crc) return unsupported(path, "a member's CRC-32 does not match its trailer");
+    if (hs[2] >= 0xfffffff0ull) return unsupported(path, "more than 2^32 lines");
+    const uint32_t NL = (uint32_t)hs[2];
     double t5 = now_s();
     f->phase_s[kPhResolve] = t5 - t4;
 
@@ -1247,24 +1306,25 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
     f->n_lines = NL;
     if (NL == 0 && T >= kRefLineLimit) return unsupported(path, "a line of 16 KiB or more");
     const size_t max_rec = (size_t)NL / 4 + 1;
-    KID_CUDA(f->nlpos.reserve(sizeof(uint32_t) * ((size_t)NL + 8)));
-    KID_CUDA(f->recs.reserve(sizeof(uint32_t) * 6 * max_rec));
+    KID_CUDA(f->nlpos.reserve(sizeof(uint64_t) * ((size_t)NL + 8)));
+    KID_CUDA(f->recs.reserve((3 * sizeof(uint64_t) + 3 * sizeof(uint32_t)) * max_rec));
     KID_CUDA(f->off.reserve(sizeof(uint64_t) * (max_rec + 1)));
     KID_CUDA(f->seq.reserve((size_t)(T / 2) + 256));
     KID_CUDA(f->qual.reserve((size_t)(T / 2) + 256));
-    uint32_t *recs = f->recs.as<uint32_t>();
-    f->rec = RecordArrays{ recs, recs + max_rec, recs + 2 * max_rec, recs + 3 * max_rec, recs + 4 * max_rec, recs + 5 * max_rec };
-    uint32_t *err = misc + 3;
+    uint64_t *rec64 = f->recs.as<uint64_t>();
+    uint32_t *rec32 = reinterpret_cast<uint32_t *>(rec64 + 3 * max_rec);
+    f->rec = RecordArrays{ rec64, rec64 + max_rec, rec64 + 2 * max_rec, rec32, rec32 + max_rec, rec32 + 2 * max_rec };
+    unsigned long long *err = reinterpret_cast<unsigned long long *>(misc + 3);
     const uint32_t line_blocks = (NL + 255) / 256;
     if (NL) {
-        kidz_nl_write_kernel<<<n_tiles, 256, 0, st>>>(f->text.as<uint8_t>(), T, tile_cnt, f->nlpos.as<uint32_t>());
+        kidz_nl_write_kernel<<<n_tiles, 256, 0, st>>>(f->text.as<uint8_t>(), T, tile_cnt, f->nlpos.as<uint64_t>());
         KID_COUNT_LAUNCH();
         KID_CUDA(f->linecnt.reserve(sizeof(uint32_t) * ((size_t)line_blocks + 8)));
         uint32_t *line_cnt = f->linecnt.as<uint32_t>();
-        kidz_line_count_kernel<<<line_blocks, 256, 0, st>>>(f->text.as<uint8_t>(), T, f->nlpos.as<uint32_t>(), NL, line_cnt, err);
+        kidz_line_count_kernel<<<line_blocks, 256, 0, st>>>(f->text.as<uint8_t>(), T, f->nlpos.as<uint64_t>(), NL, line_cnt, err);
         KID_COUNT_LAUNCH();
         KID_TRY(scan_u32<uint32_t>(f, line_cnt, nullptr, line_blocks, line_cnt, misc + 0));
-        kidz_line_write_kernel<<<line_blocks, 256, 0, st>>>(f->text.as<uint8_t>(), f->nlpos.as<uint32_t>(), NL, line_cnt, misc, f->rec, err);
+        kidz_line_write_kernel<<<line_blocks, 256, 0, st>>>(f->text.as<uint8_t>(), f->nlpos.as<uint64_t>(), NL, line_cnt, misc, f->rec, err);
         KID_COUNT_LAUNCH();
     }
     kidz_set_records_kernel<<<1, 1, 0, st>>>(misc);
@@ -1274,12 +1334,13 @@ int kid_fastq_load_gz_file(kid_fastq *f, const char *path, size_t *n_reads)
                                                                        f->seq.as<uint8_t>(), f->qual.as<uint8_t>(), err);
     KID_COUNT_LAUNCH();
     KID_CUDA(cudaGetLastError());
-    KID_CUDA(cudaMemcpyAsync(hs, misc, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, st));
+    KID_CUDA(cudaMemcpyAsync(hs, misc, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost, st));
     KID_CUDA(cudaStreamSynchronize(st));
     if (hs[3] & kErrLongLine) return unsupported(path, "a line of 16 KiB or more");
     if (hs[3] & kErrShortQual) return unsupported(path, "a quality line shorter than its read");
-    f->n_reads = hs[1];
+    f->n_reads = (size_t)hs[1];
     f->n_bases = hs[4];
+    if (kid_pack_word_index(f->n_bases, f->n_reads) + 2 >= 0x80000000ull) return unsupported(path, "more than 2^31 packed words");
     f->loaded = true;
     if (n_reads) *n_reads = f->n_reads;
     f->phase_s[kPhFrame] = now_s() - t5;

@@ -14,3 +14,4 @@ grep -v "^\[nk10\] parse\|cached" $W/gpu.err | sed -e 's#/tmp/kid_big/fq/##g' | 
 cmp $W/host.out $W/gpu.out && echo "stdout identical"
 for f in $W/keep/*; do cmp $f $W/fq/$(basename $f) && echo "$(basename $f) identical"; done
 nvidia-smi --query-gpu=memory.used --format=csv
+cd $R; timeout 900 python -m pytest tests/test_gpu_ingest.py tests/test_nk10_dropin.py -m gpu -q --tb=short -x 2>&1 | tail -3
