@@ -1,6 +1,6 @@
 #!/bin/bash
-# device reader at scale: one sample of 12 M pairs (3.8 GB of text per file, close to the 4 GiB limit of the 32-bit
-# text positions) and one of 14 M pairs (beyond it: must go to the host reader), against the host reader's outputs
+# device reader at scale: samples of 12 M and 14 M pairs (3.8 / 4.45 GB of text per file: first run with 32-bit text positions,
+# the 14 M sample went to the host reader; second run with 64-bit positions), against the host reader's outputs
 R=$GRAFT_REPO_ROOT
 W=/tmp/kid_big; mkdir -p $W; cd $W
 $R/tools/kid_synth db --golden $R/tests/golden/b10 --out $W --den 100 > /dev/null
