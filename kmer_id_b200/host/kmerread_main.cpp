@@ -37,8 +37,30 @@ bool ends_with(const std::string &s, const std::string &suffix)
 
 long long g_tct = 0;
 
+// gz FASTQ on the device (kid_fastq_*, include/kmer_id.h): inflate, framing, trim and scan in kernels; only tct
+// (:624) is kept per read here.  false = a file for the host reader (nothing was counted).  KID_GPU_INGEST=0: never.
+bool run_gz_fastq_on_device(kid_sample *smp, const std::string &path)
+{
+    static const bool enabled = !(getenv("KID_GPU_INGEST") && atoi(getenv("KID_GPU_INGEST")) == 0);
+    if (!enabled) return false;
+    static kid_fastq *fq = nullptr; // lives until exit, like the sample
+    if (!fq && kid_fastq_create(kid_sample_db(smp), &fq) != 0) return false;
+    size_t n = 0;
+    const int rc = kid_fastq_load_gz_file(fq, path.c_str(), &n);
+    if (rc == KID_EUNSUPPORTED) return false;
+    if (rc != 0) { std::cerr << "kmerread: " << kid_last_error() << std::endl; exit(1); }
+    void *p = nullptr;
+    if (kid_host_alloc(&p, sizeof(int32_t) * (n + 1)) != 0) { std::cerr << "kmerread: " << kid_last_error() << std::endl; exit(1); }
+    int32_t *taxon = (int32_t *)p;
+    if (kid_fastq_classify(fq, smp, taxon) != 0) { std::cerr << "kmerread: " << kid_last_error() << std::endl; exit(1); }
+    for (size_t r = 0; r < n; r++) g_tct += taxon[r] >= 0; // tct++ per processed read (:624)
+    kid_host_free(p);
+    return true;
+}
+
 void run_file(kid_sample *smp, ReadFormat fmt, const std::string &path)
 {
+    if (fmt == ReadFormat::GzFastq && run_gz_fastq_on_device(smp, path)) return;
     if (fmt == ReadFormat::GzFasta) std::cout << "true" << std::endl; // process_fagz :789
     ReadBatchReader reader(fmt, path, (size_t)1 << 19, (size_t)96 << 20, pipeline_batches());
     classify_stream(smp, reader, [&](const ReadBatch &b) {

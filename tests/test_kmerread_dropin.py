@@ -94,7 +94,8 @@ def test_all_input_kinds_match_reference(tmp_path):
     _write_fasta(os.path.join(d, "a.fasta"), a, width=60)
     _write_fasta(os.path.join(d, "b.fasta"), b, crlf=True, blanks=True)
     _write_fasta(os.path.join(d, "a.fasta.gz"), a, width=70, gz=True, blanks=True)
-    res = _both(ref, w, os.path.join(d, "a.fastq.gz"), os.path.join(d, "b.fastq.gz"))
+    res = _both(ref, w, os.path.join(d, "a.fastq.gz"), os.path.join(d, "b.fastq.gz"))  # gz FASTQ: read on the device
+    assert _both(ref, w, os.path.join(d, "a.fastq.gz"), os.path.join(d, "b.fastq.gz"), env={"KID_GPU_INGEST": "0"}) == res
     assert len(res.split(b"\n")) == MITO_NTAXA + 1
     g = np.array([int(l.split(b",")[1]) for l in res.split(b"\n")[:-1]])
     assert g[2:].sum() > 500
