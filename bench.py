@@ -562,7 +562,18 @@ def files_e2e(args, n_gpus=1):
         on_device = on_device_files == 2 * n_samples
         m = re.search(r"\[nk10\] parse db ([0-9.]+) s, build table ([0-9.]+) s, total ([0-9.]+) s", r.stderr)
         med = statistics.median(per_sample)
-        return {"value": pairs / med, "unit": UNIT,
+        phases = None
+        try:  # the device-side reader's own phase times per file (seconds, median over the files after the first sample)
+            rows = [dict((k, float(v)) for k, v in re.findall(r"(read|find|inflate|chain|resolve|frame|classify|fetch) (-?[0-9.]+)", ln))
+                    for ln in r.stderr.splitlines() if "on the device:" in ln][2:]
+            if rows:
+                phases = {k: statistics.median(row[k] for row in rows if k in row) for k in rows[0]}
+        except Exception:
+            phases = None
+        return {"value": pairs / med, "unit": UNIT, "reader_phase_s": phases,
+                "reader_phase_note": "host-clock seconds per file between the reader's synchronisation points, R1 and R2 "
+                                     "overlapping; find is launched with inflate and shows up there; most of it runs ahead, "
+                                     "under the previous sample",
                 "what": "kmer_id_b200/bin/nk10: gz FASTQ on disk -> _result.txt/_reads.txt, MEDIAN of %d samples in one "
                         "process (%s); probe DB parsed from gz text"
                         % (n_samples, "compressed bytes to the GPU: inflate, line framing, trim, pack and classify in kernels, "
