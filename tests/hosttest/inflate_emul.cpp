@@ -1,7 +1,8 @@
 // inflate_emul.cpp - runs the device-side inflate of kmer_id_b200/csrc/kid_inflate.cuh on the CPU, step
 // by step the way kid_ingest.cu runs it on the GPU (find -> inflate per piece -> chain -> window maps in
 // groups -> resolve -> CRC-32 in chunks), and compares the text with zlib's.  Test infrastructure.
-//   inflate_emul FILE.gz [piece_bytes [expand [group]]]      exit 0 = identical (or cleanly refused with -r)
+//   inflate_emul FILE.gz [piece_bytes [expand [group]]]      exit 0 = identical, 3 = cleanly refused
+//   KIDZ_TEXT_ONLY=1: the block finder's text-only filter; KIDZ_WARP=1: the warp-per-piece decoder (emulated)
 #include "../../kmer_id_b200/csrc/kid_inflate_chain.hpp"
 
 #include <chrono>
@@ -14,6 +15,116 @@
 
 using namespace kidz;
 
+// ---- the warp-per-piece decoder of kid_ingest.cu (warp_symbols / warp_inflate_piece), its 32 lanes played one
+// after the other: every lane decodes the token that would start at "its" bit, the real tokens are the chain
+// from lane 0, block headers and tokens the fast tables do not cover go through the plain decoder.  A
+// restatement for the CPU (the device code uses shuffles and cannot be compiled here), statement by statement.
+enum { kRoundEob = 0, kRoundBad = 1, kRoundOverflow = 2, kRoundSlowToken = 3 };
+
+static int warp_symbols_emul(const uint32_t *w, uint64_t size_bits, Tab<1> t, uint16_t *out, uint64_t &bp, int32_t &pos, int32_t floor,
+                             int32_t cap)
+{
+    for (;;) {
+        if (bp > size_bits) return kRoundBad;
+        uint32_t bits[32], outlen[32], code[32], kind[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            const uint64_t b = bp + lane;
+            const uint32_t lo = peek32(w, b), hi = peek32(w, b + 32);
+            const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+            const uint32_t e = t.at(kOffLitFast + (int)(lo & ((1u << kLitRoot) - 1u)));
+            bits[lane] = e & 15u;
+            outlen[lane] = 1;
+            code[lane] = e >> 4;
+            kind[lane] = 0;
+            if (bits[lane] == 0 || code[lane] > 285u) kind[lane] = 3;
+            else if (code[lane] == 256u) { kind[lane] = 2; outlen[lane] = 0; }
+            else if (code[lane] > 256u) {
+                uint32_t len;
+                const uint32_t c = code[lane];
+                if (c < 265u) len = c - 254u;
+                else if (c == 285u) len = 258u;
+                else {
+                    const uint32_t x = c - 261u, eb = x >> 2;
+                    len = 3u + ((4u + (x & 3u)) << eb) + ((uint32_t)(v >> bits[lane]) & ((1u << eb) - 1u));
+                    bits[lane] += eb;
+                }
+                const uint32_t de = t.at(kOffDistFast + (int)((uint32_t)(v >> bits[lane]) & ((1u << kDistRoot) - 1u)));
+                const uint32_t ds = de >> 4;
+                if ((de & 15u) == 0 || ds > 29u) kind[lane] = 3;
+                else {
+                    bits[lane] += de & 15u;
+                    uint32_t dist;
+                    if (ds < 4u) dist = ds + 1u;
+                    else {
+                        const uint32_t eb = (ds >> 1) - 1u;
+                        dist = 1u + ((2u + (ds & 1u)) << eb) + ((uint32_t)(v >> bits[lane]) & ((1u << eb) - 1u));
+                        bits[lane] += eb;
+                    }
+                    kind[lane] = 1;
+                    outlen[lane] = len;
+                    code[lane] = kCopyFlag | (dist - 1u);
+                }
+            }
+        }
+        uint32_t cur = 0, total = 0;
+        int32_t at[32];
+        bool on[32] = { false }, eob = false;
+        while (cur < 32u) {
+            const uint32_t kd = kind[cur];
+            if (kd == 3u) break;
+            on[cur] = true;
+            at[cur] = pos + (int32_t)total;
+            total += outlen[cur];
+            cur = cur + bits[cur];
+            if (kd == 2u) { eob = true; break; }
+        }
+        if (total == 0 && !eob && cur == 0) return kRoundSlowToken;
+        if (total > (uint32_t)(cap - pos)) return kRoundOverflow;
+        for (uint32_t lane = 0; lane < 32; lane++)
+            if (on[lane] && kind[lane] == 1u && (int32_t)((code[lane] & 0x7fffu) + 1u) > at[lane] - floor) return kRoundBad;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            if (!on[lane]) continue;
+            if (kind[lane] == 0u) out[at[lane]] = (uint16_t)code[lane];
+            if (kind[lane] == 1u)
+                for (uint32_t i = 0; i < outlen[lane]; i++) out[at[lane] + (int32_t)i] = (uint16_t)code[lane];
+        }
+        pos += (int32_t)total;
+        bp += cur;
+        if (eob) return kRoundEob;
+    }
+}
+
+static void warp_inflate_piece_emul(const uint32_t *w, uint64_t size, uint64_t start_bit, uint64_t stop_bit, int floor0, uint16_t *out,
+                                    uint32_t out_cap, Tab<1> tab, PieceResult &res)
+{
+    Inflater<1> d;
+    d.start(w, size, start_bit, stop_bit, floor0, out, out_cap, tab, &res);
+    for (;;) {
+        if (d.state == Inflater<1>::kAtBoundary) d.block_header();
+        if (d.state == Inflater<1>::kDone) break;
+        if (d.state == Inflater<1>::kAtBoundary) continue;
+        uint64_t bp = d.in.pos();
+        int32_t pos = d.pos;
+        const int rc = warp_symbols_emul(w, size * 8, tab, out, bp, pos, d.floor, (int32_t)out_cap);
+        d.pos = pos;
+        d.in.seek(w, bp);
+        if (rc == kRoundEob) d.end_of_block();
+        else if (rc == kRoundBad) d.refuse(kPieceBadData);
+        else if (rc == kRoundOverflow) d.refuse(kPieceOverflow);
+        else {
+            d.symbol();
+            while (d.fill_left) d.write_fill();
+        }
+    }
+}
+
+static void inflate_one(bool warp, const uint32_t *w, uint64_t size, uint64_t start_bit, uint64_t stop_bit, int floor0, uint16_t *out,
+                        uint32_t out_cap, Tab<1> tab, PieceResult &res)
+{
+    if (warp) warp_inflate_piece_emul(w, size, start_bit, stop_bit, floor0, out, out_cap, tab, res);
+    else inflate_piece(w, size, start_bit, stop_bit, floor0, out, out_cap, tab, res);
+}
+
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char **argv)
@@ -22,6 +133,7 @@ int main(int argc, char **argv)
     const uint64_t P = argc > 2 ? strtoull(argv[2], nullptr, 10) : 32768;
     const uint64_t expand = argc > 3 ? strtoull(argv[3], nullptr, 10) : 10;
     const size_t G = argc > 4 ? strtoull(argv[4], nullptr, 10) : 64;
+    const bool warp = getenv("KIDZ_WARP") != nullptr; // the warp-per-piece decoder instead of the plain one
     FILE *f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     std::vector<uint32_t> words;
@@ -86,7 +198,7 @@ int main(int argc, char **argv)
             n_nostart++;
             continue;
         }
-        inflate_piece(w, size, found[k], piece_end_bit(k, P, size), k == 0 ? 0 : kWin, syms.data() + k * slot, slot, tab, res[k]);
+        inflate_one(warp, w, size, found[k], piece_end_bit(k, P, size), k == 0 ? 0 : kWin, syms.data() + k * slot, slot, tab, res[k]);
         if (res[k].status == kPieceOk) resolve_copies(syms.data() + k * slot, res[k].n_out);
         if (res[k].status == kPieceBadData) n_bad++;
         if (res[k].status == kPieceOverflow) n_over++;
@@ -95,7 +207,7 @@ int main(int argc, char **argv)
     double t2 = now();
     Chain chain;
     const char *why = walk_chain(res, P, size, first_block_bit, [&](size_t k, uint64_t start) {
-        inflate_piece(w, size, start, piece_end_bit(k, P, size), kWin, syms.data() + k * slot, slot, tab, res[k]);
+        inflate_one(warp, w, size, start, piece_end_bit(k, P, size), kWin, syms.data() + k * slot, slot, tab, res[k]);
         if (res[k].status == kPieceOk) resolve_copies(syms.data() + k * slot, res[k].n_out);
         if (getenv("KIDZ_DEBUG")) fprintf(stderr, "redo piece %zu from bit %llu: status %u end %llu n_out %u\n", k, (unsigned long long)start, res[k].status, (unsigned long long)res[k].end_bit, res[k].n_out);
         return true;

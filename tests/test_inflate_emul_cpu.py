@@ -1,6 +1,7 @@
 """The device-side inflate (kmer_id_b200/csrc/kid_inflate.cuh) run on the CPU by tests/hosttest/inflate_emul.cpp
 the way kid_ingest.cu runs it on the GPU - block finder, per-piece decode to symbols + copy codes, the copy
-pass, the chain walk, grouped window maps, marker resolve, CRC-32 in chunks - against zlib on gzip files of
+pass, the chain walk, grouped window maps, marker resolve, CRC-32 in chunks - and a lane-by-lane restatement of
+the warp-per-piece decoder the device uses inside blocks, against zlib on gzip files of
 every kind a FASTQ reader meets (process_fqgz reads them through gzread, newkmer_10nx.cpp:770-780).
 Exit codes of the harness: 0 = text identical to zlib's, 3 = cleanly refused (the product then uses the host
 reader), anything else = a wrong answer."""
@@ -73,7 +74,10 @@ def test_identical_to_zlib(emul, text, tmp_path, kind, piece):
     else:
         blob = _deflate(text, strategy=zlib.Z_RLE)
     open(p, "wb").write(blob)
-    for env in ({}, {"KIDZ_TEXT_ONLY": "1"}):  # the block finder's text-only filter changes speculation, not results
+    # the block finder's text-only filter changes speculation, not results; KIDZ_WARP: the warp-per-piece decoder
+    # of kid_ingest.cu (every lane decodes the token that would start at its bit, the real ones are chained from
+    # lane 0), its lanes played one after the other on the CPU
+    for env in ({}, {"KIDZ_TEXT_ONLY": "1"}, {"KIDZ_WARP": "1"}):
         rc, out = _run(emul, p, piece, env=env)
         assert rc == 0, out
         assert "crc ok" in out and "identical to zlib's" in out
@@ -107,8 +111,9 @@ def test_refused_not_wrong(emul, text, tmp_path):
     for name, blob in cases.items():
         p = str(tmp_path / (name + ".gz"))
         open(p, "wb").write(blob)
-        rc, out = _run(emul, p)
-        assert rc == 3, (name, rc, out)
+        for env in ({}, {"KIDZ_WARP": "1"}):
+            rc, out = _run(emul, p, env=env)
+            assert rc == 3, (name, env, rc, out)
 
 
 def test_random_piece_sizes(emul, text, tmp_path):
@@ -117,5 +122,5 @@ def test_random_piece_sizes(emul, text, tmp_path):
     rnd = random.Random(11)
     for _ in range(4):
         piece = rnd.choice([1024, 3000 & ~3, 8192, 20000, 65536])
-        rc, out = _run(emul, p, piece, 12, rnd.choice([1, 3, 64]))
+        rc, out = _run(emul, p, piece, 12, rnd.choice([1, 3, 64]), env=rnd.choice([{}, {"KIDZ_WARP": "1"}]))
         assert rc == 0, (piece, out)
