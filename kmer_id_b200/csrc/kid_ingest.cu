@@ -339,10 +339,11 @@ kidz_inflate_one_kernel(const InflateArgs a, uint32_t k, uint64_t start)
 }
 
 // ------------------------------------------------------------------------------------------ copy
-// resolve_copies (kid_inflate.cuh) with one warp per piece, 32 positions at a time: a copy whose source
-// lies before the chunk is one gather load (everything before the chunk is final), one whose source lies
-// inside the chunk is chased through the lanes with shuffles (pointer jumping, <= 5 rounds).  The codes of
-// the next chunk are loaded before this chunk's gather comes back.
+// resolve_copies (kid_inflate.cuh) with one warp per piece, two chunks of 32 positions per round: a copy
+// whose source lies before the round's first position is one gather load (everything before it is final),
+// one whose source lies inside its own chunk is chased through the lanes with shuffles (pointer jumping,
+// <= 5 rounds), one of the second chunk whose source lies in the first takes it from there by shuffle.
+//
 // chase of the copies whose source lies inside the same chunk of 32 positions: sl = source lane (below
 // the lane's own), done = the lane holds its final symbol
 __device__ __forceinline__ uint32_t chase_in_chunk(uint32_t v, uint32_t sl, bool done)
